@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — ray-steps/s of the atmosphere hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...      the CPU arm (scalar C++ oracle, all host threads)
+
+A "step" = one pass of the hot path over one frame of synthetic rays. Workload at N=1 = BASELINE.json
+configs[1]: 1920x1080, 32 in-scatter steps, LUT mode, no clouds, scene "demo",
+Camera B (every ray hits the atmosphere, so ray-steps = W*H*32). N>1: weak scaling, every rank renders
+its own 1080p tile of an N-tile offscreen target (no data-path collective; the optional NCCL all-gather
+of the RGBA tiles is measured separately under "gather").
+
+`value`     : ray-steps/s, rays resident in HBM, kernel timed with CUDA events on the launch stream,
+              L2 flushed between timed iterations.
+`e2e`       : same metric through b200atmo_render_frame_host with HOST buffers (pinned): depth H2D +
+              RGBA D2H inside the timed region.
+`roofline`  : algorithmic HBM bytes (48 B/ray: 2 x float4 in, 1 x float4 out) / kernel time vs the measured
+              copy bandwidth. NB this path is FP32-issue/MUFU bound at N=32; see DESIGN.md.
+`cpu_baseline`: the oracle (kind "port": the reference has no CPU implementation) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ray_steps_per_sec"
+UNIT = "ray-steps/s"
+ALGO_BYTES_PER_RAY = 48  # 32 B in (2 x float4) + 16 B out (RGBA f32)
+FRAME_BYTES_PER_PIXEL_IN, FRAME_BYTES_PER_PIXEL_OUT = 4, 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--scatter-steps", type=int, default=32)
+    ap.add_argument("--cloud-steps", type=int, default=0)
+    ap.add_argument("--light", type=int, default=0)
+    ap.add_argument("--camera", choices=["A", "B"], default="B")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"{a.width}x{a.height} frame, {a.scatter_steps} in-scatter steps (LUT mode), "
+                    + (f"{a.cloud_steps} cloud steps light={a.light}, " if a.light else "no clouds, ")
+                    + f"scene demo (R=100,H=8,u_density=0.5), camera {a.camera}"
+                    + (" (all rays hit)" if a.camera == "B" else ""),
+        "width": a.width, "height": a.height, "scatter_steps": a.scatter_steps, "cloud_steps": a.cloud_steps,
+        "light_mode": a.light, "camera": a.camera, "rays_per_gpu": a.width * a.height,
+        "parallelism": f"screen-tile shard x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "l2": "flushed between timed iterations (256 MiB write)",
+    }
+
+
+def build_scene(a):
+    from godot_atmosphere_shader_b200 import scenes
+    p = scenes.demo_params()
+    cam = scenes.camera_b(a.width, a.height, p) if a.camera == "B" else scenes.camera_a(a.width, a.height)
+    depth = scenes.synth_depth(cam, p, a.width, a.height)
+    tex = dict(bn=scenes.blue_noise_tile())
+    if a.light:
+        tex["shape"] = scenes.shape_texture(64, seed=1)
+        tex["cube"] = scenes.coverage_cubemap(256, seed=1)
+    return p, cam, depth, tex
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (NVML sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        return {"sm_mhz": (int(np.median(self.samples)) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the scalar C++ oracle on all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_frame_runner(a, budget_s_per_step):
+    """Returns (run, info): run() renders one bounded sample with the oracle and returns (seconds, ray_steps)."""
+    from oracle import pyoracle as O
+    p, cam, depth, tex = build_scene(a)
+    otex = O.Textures(lut=O.bake_lut(p), shape=tex.get("shape"), cube_faces=tex.get("cube"), blue_noise=tex["bn"])
+    var = O.variant(a.scatter_steps, a.cloud_steps, a.light)
+    threads = O.hardware_threads()
+    w, h = a.width, a.height
+    od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
+
+    def render(sel_od, sel_dj):
+        t0 = time.perf_counter()
+        _, disc = O.render_rays(p, var, fr, otex, sel_od, sel_dj, threads=threads)
+        dt = time.perf_counter() - t0
+        return dt, int((disc == 0).sum()) * a.scatter_steps
+
+    # calibrate on 1/16 of the rows, then pick a row stride that keeps one step under the budget
+    rows = np.arange(0, h, 16)
+    idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
+    dt, _ = render(od[idx], dj[idx])
+    dt, _ = render(od[idx], dj[idx])
+    full_est = dt * 16
+    stride = 1
+    while full_est / stride > budget_s_per_step and stride < h:
+        stride *= 2
+    rows = np.arange(0, h, stride)
+    idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
+    s_od, s_dj = np.ascontiguousarray(od[idx]), np.ascontiguousarray(dj[idx])
+    info = {"cores": threads, "kind": "port",
+            "sample": (f"full {w}x{h} frame" if stride == 1 else f"every {stride}th row of the {w}x{h} frame ({len(rows)} rows)")
+                      + f", {a.scatter_steps} steps, scalar C++ oracle -O2 no-FMA, {threads} std::thread workers"}
+    return (lambda: render(s_od, s_dj)), info
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    total = a.steps + a.warmup
+    budget = max(0.02, min(2.0, 150.0 / max(total, 1)))
+    run, info = cpu_frame_runner(a, budget)
+    for _ in range(a.warmup):
+        run()
+    t_sum, steps_sum = 0.0, 0
+    for _ in range(a.steps):
+        dt, rs = run()
+        t_sum += dt
+        steps_sum += rs
+    value = steps_sum / t_sum
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_sum / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "mpixels_per_s": value / a.scatter_steps / 1e6,
+        "cpu_baseline": dict(info, value=value, unit=UNIT),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference ships no CPU implementation (GDShader only); this arm is the scalar C++ oracle port",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def load_traffic(a):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this workload."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(path))
+        key = f"{a.width}x{a.height}x{a.scatter_steps}_c{a.cloud_steps}_l{a.light}"
+        return d.get(key)
+    except Exception:
+        return None
+
+
+def run_ours(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from godot_atmosphere_shader_b200 import context
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback for the product path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w, h, N = a.width, a.height, a.scatter_steps
+    n_rays = w * h
+    p, cam, depth, tex = build_scene(a)
+
+    ctx = context.AtmosphereContext(local_rank)
+    ctx.set_params(p)
+    ctx.set_variant(N, a.cloud_steps, a.light)
+    ctx.upload_blue_noise(tex["bn"])
+    if a.light:
+        ctx.upload_shape3d(tex["shape"])
+        ctx.upload_coverage_cube(tex["cube"])
+    stream = torch.cuda.current_stream().cuda_stream
+
+    d_depth = torch.from_numpy(depth).to(dev)
+    d_od = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
+    d_dj = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
+    fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj, stream=stream)
+    d_rgba = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
+    d_disc = torch.empty((n_rays,), dtype=torch.uint8, device=dev)
+    ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, d_disc, stream=stream)
+    torch.cuda.synchronize()
+    hit_rays = int((d_disc == 0).sum().item())
+    ray_steps = hit_rays * N
+    checksum = float(d_rgba.double().sum().item())
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.zero_()
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for s, e in ev:
+            flush.zero_()  # L2 flush, outside the event pair
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        return ms, wall
+
+    sampler = ClockSampler(local_rank)
+    l0 = ctx.launch_count
+    # stretch the sampled region a little so NVML sees clocks under load
+    sampler.start()
+    ms_total, wall = timed_loop(lambda: ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None, stream=stream), a.steps, a.warmup)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - l0 - a.warmup
+
+    # max over ranks
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / a.steps
+    value = world * ray_steps / (ms_per_step * 1e-3)
+
+    # optional: compute + NCCL all-gather of the RGBA tiles (BASELINE config[4]); not part of `value`
+    gather = None
+    if world > 1:
+        gathered = torch.empty((world * n_rays, 4), dtype=torch.float32, device=dev)
+
+        def step_gather():
+            ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None, stream=stream)
+            dist.all_gather_into_tensor(gathered, d_rgba)
+
+        gms, _ = timed_loop(step_gather, max(10, a.steps // 4), 3)
+        g = torch.tensor([gms / max(10, a.steps // 4)], dtype=torch.float64, device=dev)
+        dist.all_reduce(g, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_step": float(g.item()), "value": world * ray_steps / (float(g.item()) * 1e-3), "unit": UNIT,
+                  "bytes_gathered_per_gpu": world * n_rays * 16, "collective": "ncclAllGather (torch.distributed)"}
+
+    # e2e through the host-buffer C-ABI call (pinned host memory)
+    h_depth = torch.from_numpy(depth).pin_memory()
+    h_rgba = torch.empty((n_rays, 4), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        ctx.render_frame_host(cam, h_depth, w, h, h_rgba, None)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        ctx.render_frame_host(cam, h_depth, w, h, h_rgba, None)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / a.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_ok = bool(np.array_equal(h_rgba.numpy(), d_rgba.cpu().numpy()))
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    achieved = ALGO_BYTES_PER_RAY * n_rays / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(a, world),
+        "mpixels_per_s": world * n_rays / (ms_per_step * 1e-3) / 1e6,
+        "hit_fraction": hit_rays / n_rays, "ray_steps_per_step": world * ray_steps,
+        "clocks": clocks,
+        "e2e": {"value": world * ray_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_IN,
+                "d2h_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_OUT, "ms_per_step": e2e_s * 1e3,
+                "api": "b200atmo_render_frame_host (pinned host depth in, RGBA out, 8 row bands over 2 streams)",
+                "timer": "host perf_counter around the synchronous call", "matches_device_path": e2e_ok},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(a), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_RAY * n_rays,
+                     "kernel": "render_rays_kernel<V2, no clouds>" if not a.light else "render_rays_kernel<V2, clouds>",
+                     "note": "FP32-issue/MUFU bound at N=32 by construction (1.5 B/ray-step); see DESIGN.md"},
+        "timed_wall_s": wall, "checksum": checksum,
+    }
+    if gather:
+        line["gather"] = gather
+    if world == 1 and not a.no_cpu_baseline:
+        run, info = cpu_frame_runner(a, budget_s_per_step=4.0)
+        run()
+        ts = [run() for _ in range(3)]
+        best = min(ts, key=lambda x: x[0])
+        line["cpu_baseline"] = dict(info, value=best[1] / best[0], unit=UNIT, ms_per_step=best[0] * 1e3)
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(a, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+"""ctypes front end of libb200atmo.so (the C-ABI of include/b200atmo.h).
+
+The library is the product; this file only marshals arguments. If the shared library is missing or
+no CUDA device is present every entry point raises — there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import B200AtmoCamera, B200AtmoFrame, B200AtmoParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200atmo.so")
+
+_lib = None
+
+# every symbol include/b200atmo.h declares
+EXPORTS = [
+    "b200atmo_version", "b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera", "b200atmo_create",
+    "b200atmo_destroy", "b200atmo_last_error", "b200atmo_default_params", "b200atmo_set_params", "b200atmo_get_params",
+    "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube",
+    "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
+    "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_make_rays", "b200atmo_render_frame_host",
+    "b200atmo_launch_count",
+]
+
+
+class B200AtmoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200atmo error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libb200atmo.so (built by `__graft_entry__.build()` / csrc/build.sh). Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with godot_atmosphere_shader_b200/csrc/build.sh "
+                              "(python -c 'import __graft_entry__ as g; g.build()'). There is no fallback path.")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.b200atmo_version.restype = i32
+        for f in ("b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera"):
+            getattr(L, f).restype = sz
+        L.b200atmo_create.argtypes = [i32, C.POINTER(vp)]
+        L.b200atmo_destroy.argtypes = [vp]
+        L.b200atmo_destroy.restype = None
+        L.b200atmo_last_error.argtypes = [vp]
+        L.b200atmo_last_error.restype = C.c_char_p
+        L.b200atmo_default_params.argtypes = [C.POINTER(B200AtmoParams)]
+        L.b200atmo_default_params.restype = None
+        L.b200atmo_set_params.argtypes = [vp, C.POINTER(B200AtmoParams)]
+        L.b200atmo_get_params.argtypes = [vp, C.POINTER(B200AtmoParams)]
+        L.b200atmo_set_variant.argtypes = [vp, i32, i32, i32, i32]
+        L.b200atmo_upload_blue_noise.argtypes = [vp, vp, i32, i32]
+        L.b200atmo_upload_shape3d.argtypes = [vp, vp, i32, i32, i32]
+        L.b200atmo_upload_coverage_cube.argtypes = [vp, vp, i32]
+        L.b200atmo_bake_optical_depth.argtypes = [vp, vp]
+        L.b200atmo_download_lut.argtypes = [vp, vp]
+        L.b200atmo_download_cube_padded.argtypes = [vp, vp, sz, C.POINTER(i32)]
+        L.b200atmo_render_rays.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, sz, vp, vp, vp]
+        L.b200atmo_render_rays_host.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, sz, vp, vp]
+        L.b200atmo_render_frame.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, vp, vp]
+        L.b200atmo_make_rays.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, C.POINTER(B200AtmoFrame), vp]
+        L.b200atmo_render_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp]
+        L.b200atmo_launch_count.argtypes = [vp]
+        L.b200atmo_launch_count.restype = C.c_uint64
+        for name in EXPORTS:
+            getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        _lib = L
+    return _lib
+
+
+def _dptr(x):
+    """Device/host pointer of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+class AtmosphereContext:
+    """One context per device; owns the LUT and the textures (include/b200atmo.h conventions)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().b200atmo_create(int(device), C.byref(self._h))
+        if rc != abi.OK:
+            raise B200AtmoError(rc, lib().b200atmo_last_error(None).decode())
+        self.device = device
+        self._cube_res = 1  # the context starts with a 1x1 white cube (unset sampler)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200atmo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != abi.OK:
+            raise B200AtmoError(rc, lib().b200atmo_last_error(self._h).decode())
+
+    # ---- uniforms ----
+    def set_params(self, p: B200AtmoParams):
+        self._check(lib().b200atmo_set_params(self._h, C.byref(p)))
+
+    def get_params(self) -> B200AtmoParams:
+        p = B200AtmoParams()
+        self._check(lib().b200atmo_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_variant(self, scatter_steps=8, cloud_steps=0, light_mode=abi.LIGHT_NONE, scatter_model=abi.SCATTER_V2):
+        self._check(lib().b200atmo_set_variant(self._h, scatter_model, scatter_steps, cloud_steps, light_mode))
+
+    # ---- textures ----
+    def upload_blue_noise(self, tex: np.ndarray):
+        t = np.ascontiguousarray(tex, dtype=np.uint8)
+        self._check(lib().b200atmo_upload_blue_noise(self._h, t.ctypes.data, t.shape[1], t.shape[0]))
+
+    def upload_shape3d(self, tex: np.ndarray):
+        t = np.ascontiguousarray(tex, dtype=np.uint8)
+        nz, ny, nx = t.shape
+        self._check(lib().b200atmo_upload_shape3d(self._h, t.ctypes.data, nx, ny, nz))
+
+    def upload_coverage_cube(self, faces: np.ndarray):
+        t = np.ascontiguousarray(faces, dtype=np.uint8)
+        assert t.ndim == 3 and t.shape[0] == 6 and t.shape[1] == t.shape[2]
+        self._check(lib().b200atmo_upload_coverage_cube(self._h, t.ctypes.data, t.shape[1]))
+        self._cube_res = int(t.shape[1])
+
+    # ---- LUT ----
+    def bake_optical_depth(self, stream=None):
+        self._check(lib().b200atmo_bake_optical_depth(self._h, stream))
+
+    def download_lut(self) -> np.ndarray:
+        out = np.empty((abi.LUT_SIZE, abi.LUT_SIZE), dtype=np.float32)
+        self._check(lib().b200atmo_download_lut(self._h, out.ctypes.data))
+        return out
+
+    def download_cube_padded(self) -> np.ndarray:
+        r = self._cube_res
+        buf = np.empty((6, r + 2, r + 2), dtype=np.uint8)
+        res = C.c_int(0)
+        self._check(lib().b200atmo_download_cube_padded(self._h, buf.ctypes.data, buf.size, C.byref(res)))
+        assert res.value == r
+        return buf
+
+    # ---- rendering ----
+    def render_rays(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, rgba, discard=None, stream=None):
+        self._check(lib().b200atmo_render_rays(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
+                                               _dptr(rgba), _dptr(discard), stream))
+
+    def render_rays_host(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, rgba, discard=None):
+        self._check(lib().b200atmo_render_rays_host(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
+                                                    _dptr(rgba), _dptr(discard)))
+
+    def render_frame(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, row_begin=0, row_end=None, stream=None):
+        self._check(lib().b200atmo_render_frame(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
+                                                int(h if row_end is None else row_end), _dptr(rgba), _dptr(discard), stream))
+
+    def make_rays(self, cam: B200AtmoCamera, depth, w, h, origin_depth, dir_jitter, stream=None) -> B200AtmoFrame:
+        fr = B200AtmoFrame()
+        self._check(lib().b200atmo_make_rays(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(origin_depth),
+                                             _dptr(dir_jitter), C.byref(fr), stream))
+        return fr
+
+    def render_frame_host(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None):
+        self._check(lib().b200atmo_render_frame_host(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
+                                                     _dptr(discard)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().b200atmo_launch_count(self._h))

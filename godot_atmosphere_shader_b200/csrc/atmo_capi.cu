@@ -1,0 +1,493 @@
+// C-ABI of include/b200atmo.h: context, uniforms, texture uploads, LUT bake, ray-batch and frame
+// entry points. Host code only (the kernels live in atmo_kernels.cu). There is no CPU fallback:
+// every compute entry point launches CUDA kernels or fails with B200ATMO_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "atmo_consts.h"
+#include "atmo_internal.h"
+
+using namespace b200atmo;
+
+struct b200atmo_ctx {
+    int device = 0;
+    B200AtmoParams params;
+    Variant variant;
+    bool lut_stale = true;
+    float* d_lut = nullptr;       // [256][256]
+    float* d_lut_pad = nullptr;   // [258][258]
+    uint8_t* d_cube_raw = nullptr;
+    uint8_t* d_cube_pad_u8 = nullptr;
+    float* d_cube_pad = nullptr;
+    int cube_res = 0;
+    uint8_t* d_shape_raw = nullptr;
+    float* d_shape_pad = nullptr;
+    int nx = 0, ny = 0, nz = 0;
+    uint8_t* d_blue = nullptr;
+    int bn_w = 0, bn_h = 0;
+    // staging for the host-buffer entry points (grown on demand, reused across calls)
+    void* d_stage_in0 = nullptr;
+    void* d_stage_in1 = nullptr;
+    void* d_stage_out = nullptr;
+    uint8_t* d_stage_disc = nullptr;
+    size_t cap_in0 = 0, cap_in1 = 0, cap_out = 0, cap_disc = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    std::string last_error;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(b200atmo_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(ctx, _e == cudaErrorMemoryAllocation ? B200ATMO_E_NOMEM : B200ATMO_E_CUDA,            \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int ensure(b200atmo_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return B200ATMO_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CU_TRY(ctx, cudaMalloc(p, need));
+    *cap = need;
+    return B200ATMO_OK;
+}
+
+DeviceTextures textures_of(const b200atmo_ctx* ctx) {
+    DeviceTextures t;
+    t.lut_pad = ctx->d_lut_pad;
+    t.cube_pad = ctx->d_cube_pad;
+    t.cube_res = ctx->cube_res;
+    t.shape_pad = ctx->d_shape_pad;
+    t.nx = ctx->nx;
+    t.ny = ctx->ny;
+    t.nz = ctx->nz;
+    t.blue_noise = ctx->d_blue;
+    t.bn_w = ctx->bn_w;
+    t.bn_h = ctx->bn_h;
+    return t;
+}
+
+int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
+    if (!ctx->lut_stale) return B200ATMO_OK;
+    CU_TRY(ctx, launch_bake_lut(ctx->params.planet_radius, ctx->params.atmosphere_height, ctx->params.density, ctx->d_lut,
+                                ctx->d_lut_pad, s));
+    ctx->launches++;
+    // re-bakes are rare (R, H or u_density changed); finishing here keeps later launches on OTHER streams safe
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->lut_stale = false;
+    return B200ATMO_OK;
+}
+
+int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_t s) {
+    const size_t raw = size_t(6) * res * res, pad = size_t(6) * (res + 2) * (res + 2);
+    uint8_t *d_raw = nullptr, *d_pad8 = nullptr;
+    float* d_pad = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d_raw, raw));
+    CU_TRY(ctx, cudaMalloc(&d_pad8, pad));
+    CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw, h_faces6, raw, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, launch_cube_pad(d_raw, res, d_pad8, d_pad, s));
+    ctx->launches++;
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    cudaFree(ctx->d_cube_raw);
+    cudaFree(ctx->d_cube_pad_u8);
+    cudaFree(ctx->d_cube_pad);
+    ctx->d_cube_raw = d_raw;
+    ctx->d_cube_pad_u8 = d_pad8;
+    ctx->d_cube_pad = d_pad;
+    ctx->cube_res = res;
+    return B200ATMO_OK;
+}
+
+int upload_shape(b200atmo_ctx* ctx, const uint8_t* h, int nx, int ny, int nz, cudaStream_t s) {
+    const size_t raw = size_t(nx) * ny * nz, pad = size_t(nx + 2) * (ny + 2) * (nz + 2);
+    uint8_t* d_raw = nullptr;
+    float* d_pad = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d_raw, raw));
+    CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw, h, raw, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, launch_shape_pad(d_raw, nx, ny, nz, d_pad, s));
+    ctx->launches++;
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    cudaFree(ctx->d_shape_raw);
+    cudaFree(ctx->d_shape_pad);
+    ctx->d_shape_raw = d_raw;
+    ctx->d_shape_pad = d_pad;
+    ctx->nx = nx;
+    ctx->ny = ny;
+    ctx->nz = nz;
+    return B200ATMO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200atmo_version(void) { return B200ATMO_VERSION; }
+size_t b200atmo_sizeof_params(void) { return sizeof(B200AtmoParams); }
+size_t b200atmo_sizeof_frame(void) { return sizeof(B200AtmoFrame); }
+size_t b200atmo_sizeof_camera(void) { return sizeof(B200AtmoCamera); }
+
+void b200atmo_default_params(B200AtmoParams* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->planet_radius = 1.0f;
+    p->atmosphere_height = 0.1f;
+    p->density = 0.2f;
+    p->scattering_strength = 20.0f;
+    p->scattering_wavelengths[0] = 700.0f;
+    p->scattering_wavelengths[1] = 530.0f;
+    p->scattering_wavelengths[2] = 440.0f;
+    for (int k = 0; k < 3; ++k) p->atmosphere_modulate[k] = 1.0f;
+    p->atmosphere_ambient_color[2] = 0.002f;
+    p->cloud_density_scale = 50.0f;
+    p->cloud_bottom = 0.2f;
+    p->cloud_top = 0.5f;
+    p->cloud_blend = 0.5f;
+    p->cloud_shape_factor = 0.8f;
+    p->cloud_shape_scale = 1.0f;
+    p->cloud_coverage_rotation[0] = 1.0f;
+    p->cloud_coverage_rotation[3] = 1.0f;
+    for (int k = 0; k < 4; ++k) p->world_to_model[k * 5] = 1.0f;
+    const float day[4] = {0.5f, 0.8f, 1.0f, 1.0f}, night[4] = {0.2f, 0.4f, 0.8f, 1.0f};
+    for (int k = 0; k < 4; ++k) {
+        p->day_color0[k] = p->day_color1[k] = day[k];
+        p->night_color0[k] = p->night_color1[k] = night[k];
+    }
+    p->day_night_transition_scale = 2.0f;
+}
+
+int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
+    if (!out) return fail(nullptr, B200ATMO_E_INVALID, "b200atmo_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, B200ATMO_E_CUDA,
+                    std::string("b200atmo_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, B200ATMO_E_INVALID, "b200atmo_create: bad device index");
+    b200atmo_ctx* ctx = new (std::nothrow) b200atmo_ctx();
+    if (!ctx) return fail(nullptr, B200ATMO_E_NOMEM, "b200atmo_create: out of host memory");
+    ctx->device = cuda_device;
+    b200atmo_default_params(&ctx->params);
+    DeviceGuard g(cuda_device);
+    auto bail = [&](int code) {
+        g_create_error = ctx->last_error;
+        b200atmo_destroy(ctx);
+        return code;
+    };
+#define CREATE_TRY(expr)                                                                           \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+            return bail(B200ATMO_E_CUDA);                                                          \
+        }                                                                                          \
+    } while (0)
+    CREATE_TRY(cudaMalloc(&ctx->d_lut, sizeof(float) * kLut * kLut));
+    CREATE_TRY(cudaMalloc(&ctx->d_lut_pad, sizeof(float) * kLutPad * kLutPad));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[0], cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[1], cudaStreamNonBlocking));
+#undef CREATE_TRY
+    // unset samplers read as white (README.md:46: "by default they cover the whole atmosphere uniformly")
+    const uint8_t white[6] = {255, 255, 255, 255, 255, 255};
+    int rc = upload_cube(ctx, white, 1, ctx->streams[0]);
+    if (rc == B200ATMO_OK) rc = upload_shape(ctx, white, 1, 1, 1, ctx->streams[0]);
+    if (rc != B200ATMO_OK) return bail(rc);
+    *out = ctx;
+    return B200ATMO_OK;
+}
+
+void b200atmo_destroy(b200atmo_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_lut_pad);
+    cudaFree(ctx->d_cube_raw);
+    cudaFree(ctx->d_cube_pad_u8);
+    cudaFree(ctx->d_cube_pad);
+    cudaFree(ctx->d_shape_raw);
+    cudaFree(ctx->d_shape_pad);
+    cudaFree(ctx->d_blue);
+    cudaFree(ctx->d_stage_in0);
+    cudaFree(ctx->d_stage_in1);
+    cudaFree(ctx->d_stage_out);
+    cudaFree(ctx->d_stage_disc);
+    for (auto& s : ctx->streams)
+        if (s) cudaStreamDestroy(s);
+    delete ctx;
+}
+
+const char* b200atmo_last_error(const b200atmo_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int b200atmo_set_params(b200atmo_ctx* ctx, const B200AtmoParams* p) {
+    if (!ctx || !p) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_params: NULL argument");
+    // planet_atmosphere.gd:79-81,217-218,237-238,252-253: R, H and u_density invalidate the baked LUT
+    if (p->planet_radius != ctx->params.planet_radius || p->atmosphere_height != ctx->params.atmosphere_height ||
+        p->density != ctx->params.density)
+        ctx->lut_stale = true;
+    ctx->params = *p;
+    return B200ATMO_OK;
+}
+
+int b200atmo_get_params(const b200atmo_ctx* ctx, B200AtmoParams* out) {
+    if (!ctx || !out) return B200ATMO_E_INVALID;
+    *out = ctx->params;
+    return B200ATMO_OK;
+}
+
+int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps, int cloud_steps, int light_mode) {
+    if (!ctx) return B200ATMO_E_INVALID;
+    if (scatter_model != B200ATMO_SCATTER_V2 && scatter_model != B200ATMO_SCATTER_V1)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: unknown scatter model");
+    if (scatter_steps < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: scatter_steps must be >= 1");
+    if (light_mode < B200ATMO_LIGHT_NONE || light_mode > B200ATMO_LIGHT_RAYMARCHED)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: unknown light mode");
+    if (light_mode != B200ATMO_LIGHT_NONE && cloud_steps < 1)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: cloud_steps must be >= 1 when clouds are enabled");
+    ctx->variant.scatter_model = scatter_model;
+    ctx->variant.scatter_steps = scatter_steps;
+    ctx->variant.cloud_steps = cloud_steps;
+    ctx->variant.light_mode = light_mode;
+    return B200ATMO_OK;
+}
+
+int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w, int h) {
+    if (!ctx || !h_texels) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: NULL argument");
+    if (!is_pow2(w) || !is_pow2(h) || w > 4096 || h > 4096)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: sizes must be powers of two <= 4096");
+    DeviceGuard g(ctx->device);
+    uint8_t* d = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d, size_t(w) * h));
+    CU_TRY(ctx, cudaMemcpy(d, h_texels, size_t(w) * h, cudaMemcpyHostToDevice));
+    cudaFree(ctx->d_blue);
+    ctx->d_blue = d;
+    ctx->bn_w = w;
+    ctx->bn_h = h;
+    return B200ATMO_OK;
+}
+
+int b200atmo_upload_shape3d(b200atmo_ctx* ctx, const uint8_t* h_texels, int nx, int ny, int nz) {
+    if (!ctx || !h_texels) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_shape3d: NULL argument");
+    if (nx < 1 || ny < 1 || nz < 1 || nx > 1024 || ny > 1024 || nz > 1024)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_shape3d: each dimension must be in [1, 1024]");
+    DeviceGuard g(ctx->device);
+    return upload_shape(ctx, h_texels, nx, ny, nz, ctx->streams[0]);
+}
+
+int b200atmo_upload_coverage_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res) {
+    if (!ctx || !h_faces6) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_coverage_cube: NULL argument");
+    if (res < 1 || res > 4096)  // noise_cubemap.gd:30 clamps the resolution to [1, 4096]
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_coverage_cube: res must be in [1, 4096]");
+    DeviceGuard g(ctx->device);
+    return upload_cube(ctx, h_faces6, res, ctx->streams[0]);
+}
+
+int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream) {
+    if (!ctx) return B200ATMO_E_INVALID;
+    DeviceGuard g(ctx->device);
+    ctx->lut_stale = true;
+    return bake_if_stale(ctx, static_cast<cudaStream_t>(stream));
+}
+
+int b200atmo_download_lut(b200atmo_ctx* ctx, float* h_lut) {
+    if (!ctx || !h_lut) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_download_lut: NULL argument");
+    DeviceGuard g(ctx->device);
+    int rc = bake_if_stale(ctx, ctx->streams[0]);
+    if (rc != B200ATMO_OK) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(h_lut, ctx->d_lut, sizeof(float) * kLut * kLut, cudaMemcpyDeviceToHost, ctx->streams[0]));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
+    return B200ATMO_OK;
+}
+
+int b200atmo_download_cube_padded(b200atmo_ctx* ctx, uint8_t* h_out, size_t cap, int* out_res) {
+    if (!ctx || !h_out) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_download_cube_padded: NULL argument");
+    const size_t need = size_t(6) * (ctx->cube_res + 2) * (ctx->cube_res + 2);
+    if (cap < need) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_download_cube_padded: buffer too small");
+    DeviceGuard g(ctx->device);
+    CU_TRY(ctx, cudaMemcpy(h_out, ctx->d_cube_pad_u8, need, cudaMemcpyDeviceToHost));
+    if (out_res) *out_res = ctx->cube_res;
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
+                         size_t n_rays, float* d_rgba, uint8_t* d_discard, void* stream) {
+    if (!ctx || !frame) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays: NULL ctx/frame");
+    if (n_rays == 0) return B200ATMO_OK;
+    if (!d_origin_depth || !d_dir_jitter || !d_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays: NULL buffer");
+    if (n_rays > (size_t(1) << 38)) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays: n_rays too large");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = bake_if_stale(ctx, s);
+    if (rc != B200ATMO_OK) return rc;
+    DevConsts c;
+    consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));
+    consts_set_frame(c, ctx->params, frame->planet_center_view, frame->sun_center_view, frame->inv_view);
+    RayIO io{};
+    io.origin_depth = d_origin_depth;
+    io.dir_jitter = d_dir_jitter;
+    io.rgba = d_rgba;
+    io.discard = d_discard;
+    io.n = n_rays;
+    CU_TRY(ctx, launch_render_rays(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* h_origin_depth,
+                              const float* h_dir_jitter, size_t n_rays, float* h_rgba, uint8_t* h_discard) {
+    if (!ctx || !frame) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_host: NULL ctx/frame");
+    if (n_rays == 0) return B200ATMO_OK;
+    if (!h_origin_depth || !h_dir_jitter || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_host: NULL buffer");
+    DeviceGuard g(ctx->device);
+    const size_t bytes = n_rays * 4 * sizeof(float);
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_in0, &ctx->cap_in0, bytes)) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_in1, &ctx->cap_in1, bytes)) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, bytes)) != B200ATMO_OK) return rc;
+    if (h_discard && (rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_stage_disc), &ctx->cap_disc, n_rays)) != B200ATMO_OK) return rc;
+    // chunked, double-buffered over two streams so H2D, compute and D2H overlap (PCIe is full duplex)
+    const size_t chunk = (n_rays + 7) / 8 < 65536 ? n_rays : (n_rays + 7) / 8;
+    int k = 0;
+    for (size_t b = 0; b < n_rays; b += chunk, ++k) {
+        const size_t m = (n_rays - b < chunk) ? n_rays - b : chunk;
+        cudaStream_t s = ctx->streams[k & 1];
+        float* in0 = static_cast<float*>(ctx->d_stage_in0) + 4 * b;
+        float* in1 = static_cast<float*>(ctx->d_stage_in1) + 4 * b;
+        float* out = static_cast<float*>(ctx->d_stage_out) + 4 * b;
+        CU_TRY(ctx, cudaMemcpyAsync(in0, h_origin_depth + 4 * b, m * 16, cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(in1, h_dir_jitter + 4 * b, m * 16, cudaMemcpyHostToDevice, s));
+        rc = b200atmo_render_rays(ctx, frame, in0, in1, m, out, h_discard ? ctx->d_stage_disc + b : nullptr, s);
+        if (rc != B200ATMO_OK) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(h_rgba + 4 * b, out, m * 16, cudaMemcpyDeviceToHost, s));
+        if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard + b, ctx->d_stage_disc + b, m, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
+    return B200ATMO_OK;
+}
+
+static int frame_consts(b200atmo_ctx* ctx, const B200AtmoCamera* cam, int w, int h, int row_begin, int row_end, DevConsts& c) {
+    if (w < 1 || h < 1 || row_begin < 0 || row_end > h || row_begin > row_end)
+        return fail(ctx, B200ATMO_E_INVALID, "frame: bad size / row range");
+    consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));
+    consts_set_camera(c, ctx->params, *cam, w, h, row_begin, row_end);
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                          int row_end, float* d_rgba, uint8_t* d_discard, void* stream) {
+    if (!ctx || !cam || !d_depth || !d_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DevConsts c;
+    int rc = frame_consts(ctx, cam, w, h, row_begin, row_end, c);
+    if (rc != B200ATMO_OK) return rc;
+    if (row_begin == row_end) return B200ATMO_OK;
+    if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
+    consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));  // LUT pointer is stable; refresh anyway
+    consts_set_camera(c, ctx->params, *cam, w, h, row_begin, row_end);
+    RayIO io{};
+    io.depth = d_depth;
+    io.rgba = d_rgba;
+    io.discard = d_discard;
+    io.n = size_t(w) * h;
+    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, float* d_origin_depth,
+                       float* d_dir_jitter, B200AtmoFrame* frame_out, void* stream) {
+    if (!ctx || !cam || !d_depth || !d_origin_depth || !d_dir_jitter)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_make_rays: NULL argument");
+    DeviceGuard g(ctx->device);
+    DevConsts c;
+    int rc = frame_consts(ctx, cam, w, h, 0, h, c);
+    if (rc != B200ATMO_OK) return rc;
+    RayIO io{};
+    io.depth = d_depth;
+    io.out_origin_depth = d_origin_depth;
+    io.out_dir_jitter = d_dir_jitter;
+    io.n = size_t(w) * h;
+    CU_TRY(ctx, launch_make_rays(c, io, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
+    if (frame_out) {
+        // the varyings of atmosphere_vertex (main:101-103) + the (fixed-up) INV_VIEW_MATRIX
+        float world_pos[4], pc[4], sc[4];
+        hostmath::mat4_mul_vec(cam->model, 0.0f, 0.0f, 0.0f, 1.0f, world_pos);
+        hostmath::mat4_mul_vec(cam->view, world_pos[0], world_pos[1], world_pos[2], world_pos[3], pc);
+        hostmath::mat4_mul_vec(cam->view, ctx->params.sun_position[0], ctx->params.sun_position[1], ctx->params.sun_position[2],
+                               1.0f, sc);
+        for (int k = 0; k < 3; ++k) {
+            frame_out->planet_center_view[k] = pc[k];
+            frame_out->sun_center_view[k] = sc[k];
+        }
+        std::memcpy(frame_out->inv_view, c.inv_view_ray, sizeof(frame_out->inv_view));
+    }
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h, float* h_rgba,
+                               uint8_t* h_discard) {
+    if (!ctx || !cam || !h_depth || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host: NULL argument");
+    if (w < 1 || h < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host: bad size");
+    DeviceGuard g(ctx->device);
+    const size_t npx = size_t(w) * h;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_in0, &ctx->cap_in0, npx * sizeof(float))) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, npx * 4 * sizeof(float))) != B200ATMO_OK) return rc;
+    if (h_discard && (rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_stage_disc), &ctx->cap_disc, npx)) != B200ATMO_OK) return rc;
+    float* d_depth = static_cast<float*>(ctx->d_stage_in0);
+    float* d_rgba = static_cast<float*>(ctx->d_stage_out);
+    // row bands, double-buffered over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band)
+    const int bands = h >= 64 ? 8 : 1;
+    for (int k = 0; k < bands; ++k) {
+        const int r0 = int((long long)h * k / bands), r1 = int((long long)h * (k + 1) / bands);
+        if (r0 == r1) continue;
+        cudaStream_t s = ctx->streams[k & 1];
+        const size_t off = size_t(r0) * w, cnt = size_t(r1 - r0) * w;
+        CU_TRY(ctx, cudaMemcpyAsync(d_depth + off, h_depth + off, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = b200atmo_render_frame(ctx, cam, d_depth, w, h, r0, r1, d_rgba, h_discard ? ctx->d_stage_disc : nullptr, s);
+        if (rc != B200ATMO_OK) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(h_rgba + 4 * off, d_rgba + 4 * off, cnt * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard + off, ctx->d_stage_disc + off, cnt, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
+    return B200ATMO_OK;
+}
+
+uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

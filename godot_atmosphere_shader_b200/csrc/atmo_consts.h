@@ -1,0 +1,141 @@
+// Host-side derivation of the per-frame kernel constants (DevConsts) from the uniform block.
+// Plain fp32 C++ in the shader's op order; the including TU must be compiled without FMA
+// contraction (-ffp-contract=off) so the values are what the shader computes per fragment.
+#pragma once
+
+#include <cmath>
+#include <cstring>
+
+#include "atmo_internal.h"
+
+namespace b200atmo {
+
+struct Variant {
+    int scatter_model = B200ATMO_SCATTER_V2;
+    int scatter_steps = 8;   // ATMOSPHERE_RAYMARCH_STEPS of planet_atmosphere_no_clouds.gdshader:4
+    int cloud_steps = 0;
+    int light_mode = B200ATMO_LIGHT_NONE;
+};
+
+struct DeviceTextures {
+    const float* lut_pad = nullptr;
+    const float* cube_pad = nullptr;
+    int cube_res = 0;
+    const float* shape_pad = nullptr;
+    int nx = 0, ny = 0, nz = 0;
+    const uint8_t* blue_noise = nullptr;
+    int bn_w = 0, bn_h = 0;
+};
+
+namespace hostmath {
+inline void mat4_mul_vec(const float* m, float x, float y, float z, float w, float out[4]) {
+    for (int r = 0; r < 4; ++r) out[r] = m[0 + r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
+}
+// (a*b)[col][row] = sum_k a[k][row]*b[col][k], k ascending — GLSL mat4*mat4
+inline void mat4_mul_mat(const float* a, const float* b, float* out) {
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 4; ++row)
+            out[col * 4 + row] = a[0 + row] * b[col * 4 + 0] + a[4 + row] * b[col * 4 + 1] + a[8 + row] * b[col * 4 + 2] +
+                                 a[12 + row] * b[col * 4 + 3];
+}
+inline float pow4(float x) { return x * x * x * x; }
+}  // namespace hostmath
+
+// Uniform-only part (everything that does not depend on the frame).
+inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Variant& v, const DeviceTextures& t) {
+    std::memset(&c, 0, sizeof(c));
+    c.R = p.planet_radius;
+    c.H = p.atmosphere_height;
+    c.rho = p.density;
+    c.atmo_radius = p.planet_radius + p.atmosphere_height;  // main:144
+    c.sphere_depth_factor = p.sphere_depth_factor;
+    for (int k = 0; k < 3; ++k) {
+        c.coef[k] = hostmath::pow4(400.0f / p.scattering_wavelengths[k]) * p.scattering_strength;  // funcs_v2:47-51
+        c.neg_coef_log2e[k] = -c.coef[k] * 1.4426950408889634f;
+        c.ambient[k] = p.atmosphere_ambient_color[k];
+        c.modulate[k] = p.atmosphere_modulate[k];
+        c.day0[k] = p.day_color0[k];
+        c.day1[k] = p.day_color1[k];
+        c.night0[k] = p.night_color0[k];
+        c.night1[k] = p.night_color1[k];
+    }
+    c.inv_H = 1.0f / c.H;
+    c.rho2 = c.rho * c.rho;
+    c.day_night_scale = p.day_night_transition_scale;
+    c.lut_pad = t.lut_pad;
+    // clouds
+    c.cloud_bottom_h = p.planet_radius + p.cloud_bottom * p.atmosphere_height;  // cloud_funcs:260
+    c.cloud_top_h = p.planet_radius + p.cloud_top * p.atmosphere_height;        // cloud_funcs:261
+    c.cloud_thickness = c.cloud_top_h - c.cloud_bottom_h;
+    c.inv_cloud_thickness = 1.0f / c.cloud_thickness;
+    c.density_scale = p.cloud_density_scale;
+    c.cloud_blend = p.cloud_blend;
+    c.coverage_bias = p.cloud_coverage_bias;
+    c.shape_factor = p.cloud_shape_factor;
+    c.shape_scale = p.cloud_shape_scale;
+    c.shape_invert = (p.cloud_shape_invert == 1.0f) ? 1 : 0;                     // cloud_funcs:57
+    for (int k = 0; k < 4; ++k) c.rot[k] = p.cloud_coverage_rotation[k];
+    {
+        const float ratio = c.R / c.cloud_top_h;                                 // ground_height / top_height
+        c.march_space = 0.5f * std::sqrt(1.0f - ratio * ratio) * c.cloud_bottom_h;  // cloud_funcs:186-189
+        c.march_ground = 3.0f * c.march_space;                                   // :190
+        c.march_hmin = c.cloud_bottom_h;                                         // :191
+        c.march_hmax = c.cloud_top_h * 1.05f;                                    // :192
+        c.light_reach = (c.cloud_top_h - c.cloud_bottom_h) * 0.15f;              // :108
+    }
+    c.cube_pad = t.cube_pad;
+    c.cube_res = t.cube_res;
+    c.shape_pad = t.shape_pad;
+    c.shape_nx = t.nx;
+    c.shape_ny = t.ny;
+    c.shape_nz = t.nz;
+    c.blue_noise = t.blue_noise;
+    c.bn_w = t.bn_w;
+    c.bn_h = t.bn_h;
+    c.scatter_steps = v.scatter_steps;
+    c.cloud_steps = v.cloud_steps > 0 ? v.cloud_steps : 1;
+}
+
+// Frame-dependent part: the varyings (planet/sun centre in view space) and INV_VIEW_MATRIX.
+inline void consts_set_frame(DevConsts& c, const B200AtmoParams& p, const float planet_center_view[3],
+                             const float sun_center_view[3], const float inv_view[16]) {
+    float v[3];
+    for (int k = 0; k < 3; ++k) {
+        c.C[k] = planet_center_view[k];
+        v[k] = sun_center_view[k] - planet_center_view[k];
+    }
+    const float len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int k = 0; k < 3; ++k) c.sun_dir[k] = v[k] / len;                       // main:164
+    hostmath::mat4_mul_mat(p.world_to_model, inv_view, c.v2m);                   // cloud_funcs:285
+    float s4[4];
+    hostmath::mat4_mul_vec(c.v2m, c.sun_dir[0], c.sun_dir[1], c.sun_dir[2], 0.0f, s4);  // cloud_funcs:288
+    for (int k = 0; k < 3; ++k) c.sun_dir_model[k] = s4[k];
+}
+
+// Frame API: derive the varyings like atmosphere_vertex (main:101-103) and the ray-generation matrices.
+inline void consts_set_camera(DevConsts& c, const B200AtmoParams& p, const B200AtmoCamera& cam, int w, int h, int row_begin,
+                              int row_end) {
+    float world_pos[4], pc[4], sc[4];
+    hostmath::mat4_mul_vec(cam.model, 0.0f, 0.0f, 0.0f, 1.0f, world_pos);
+    hostmath::mat4_mul_vec(cam.view, world_pos[0], world_pos[1], world_pos[2], world_pos[3], pc);
+    hostmath::mat4_mul_vec(cam.view, p.sun_position[0], p.sun_position[1], p.sun_position[2], 1.0f, sc);
+    float inv_view[16];
+    std::memcpy(inv_view, cam.inv_view, sizeof(inv_view));
+    if (cam.double_precision) {  // main:118-125
+        inv_view[12] *= -1.0f;
+        inv_view[13] *= -1.0f;
+        inv_view[14] *= -1.0f;
+    }
+    consts_set_frame(c, p, pc, sc, inv_view);
+    std::memcpy(c.inv_proj, cam.inv_projection, sizeof(c.inv_proj));
+    std::memcpy(c.inv_view_ray, inv_view, sizeof(c.inv_view_ray));
+    float cp[4];
+    hostmath::mat4_mul_vec(inv_view, 0.0f, 0.0f, 0.0f, 1.0f, cp);                // main:136
+    for (int k = 0; k < 3; ++k) c.cam_pos_world[k] = cp[k];
+    c.fw = w;
+    c.fh = h;
+    c.row_begin = row_begin;
+    c.row_end = row_end;
+}
+
+}  // namespace b200atmo

@@ -1,0 +1,452 @@
+// Device functions of the atmosphere hot path (sm_100a). Included by atmo_kernels.cu.
+//
+// NUMERIC POLICY. The translation unit is compiled with -fmad=false, so every expression written
+// with plain * + - / sqrtf is IEEE fp32 with no FMA contraction, i.e. bit-identical to the scalar
+// shader arithmetic. That "exact" style is used wherever rounding is amplified downstream:
+//   * per-ray set-up and every hit / miss / visibility decision (ray_sphere, t_begin/t_end, cloud test)
+//   * ray positions (pos0, pos += dir*step) — height = |pos-C| - R cancels 1-2 digits
+//   * the cloud height curve (its output is multiplied by 50 and thresholded)
+//   * texture coordinates (a 1e-7 coordinate error times a texel-to-texel slope times 135 is visible)
+//   * the LUT bake
+// FMA (fmaf) and MUFU approximations (ex2/rsqrt/rcp.approx) are requested explicitly, only in the
+// accumulation arithmetic of the hot loops, where errors do not amplify.
+//
+// The file also compiles as plain C++ (tests/hostsim) so host-side logic tests can run without a GPU;
+// that build is test infrastructure and is never loaded by the product.
+//
+// Reference being implemented (addons/zylann.atmosphere/shaders/...):
+//   include/planet_atmosphere_main.gdshaderinc:106-197  atmosphere_fragment      -> shade_ray / make_ray
+//   include/atmosphere_funcs_v2.gdshaderinc:14-101       compute_atmosphere_v2    -> scatter_v2
+//   include/atmosphere_funcs_v1.gdshaderinc:15-63        compute_atmosphere       -> scatter_v1
+//   include/cloud_funcs.gdshaderinc:25-324               render_clouds & friends  -> render_clouds
+#pragma once
+
+#include "atmo_internal.h"
+
+#define B200_PRAGMA(x) _Pragma(#x)
+#ifdef __CUDACC__
+#define B200_DEV __device__ __forceinline__
+#define B200_UNROLL(n) B200_PRAGMA(unroll n)
+#else
+#define B200_UNROLL(n)
+// ---- host simulation shims (tests/hostsim only) ----
+#include <cmath>
+#include <cstring>
+#define B200_DEV static inline
+struct float4 {
+    float x, y, z, w;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float __ldg(const float* p) { return *p; }
+static inline float __saturatef(float x) { return x != x ? 0.0f : (x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x)); }
+static inline int __float_as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+#endif
+
+namespace b200atmo {
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers (exact arithmetic: no fmaf here)
+// ------------------------------------------------------------------------------------------------
+struct f3 {
+    float x, y, z;
+};
+struct f2 {
+    float x, y;
+};
+B200_DEV f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+B200_DEV f3 ld3(const float* p) { return f3{p[0], p[1], p[2]}; }
+B200_DEV f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+B200_DEV f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+B200_DEV f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+B200_DEV f3 operator*(float s, f3 a) { return f3{s * a.x, s * a.y, s * a.z}; }
+B200_DEV float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+B200_DEV float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }  // GLSL mix
+B200_DEV float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+B200_DEV float smoothstepf(float e0, float e1, float x) {
+    float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+// mat4 (column-major) * vec4 in the shader's summation order
+B200_DEV void mat4_mul(const float* m, float x, float y, float z, float w, float out[4]) {
+    for (int r = 0; r < 4; ++r) out[r] = m[0 + r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// approximate hardware ops (MUFU), used only where stated
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+B200_DEV float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+B200_DEV float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+B200_DEV float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#else
+B200_DEV float ex2_approx(float x) { return exp2f(x); }
+B200_DEV float rsqrt_approx(float x) { return 1.0f / sqrtf(x); }
+B200_DEV float rcp_approx(float x) { return 1.0f / x; }
+#endif
+
+// sqrt(x) and 1/sqrt(x) from ONE MUFU op: rsqrt.approx + one Newton step on the root with an exact
+// (fma) residual. The pre-rounding error is ~2^-44, so the result equals IEEE sqrtf except when the
+// true root lies within that distance of a rounding midpoint (~1e-6 of inputs, then 1 ulp off).
+B200_DEV float sqrt_refined(float x, float& inv) {
+    inv = rsqrt_approx(x);
+    const float r = x * inv;
+    const float e = fmaf(-r, r, x);
+    return fmaf(e, 0.5f * inv, r);
+}
+// a/b given rb ~ 1/b (correctly rounded or 1-ulp approximate): q0 = a*rb, one exact-residual
+// correction. Equals the IEEE quotient except for the same ~1e-6 near-midpoint cases.
+B200_DEV float div_refined(float a, float b, float rb) {
+    const float q = a * rb;
+    const float r = fmaf(-q, b, a);
+    return fmaf(r, rb, q);
+}
+// floor(x) for |x| < 2^22 without the conversion pipe: round-to-nearest of x-0.5 through the
+// 1.5*2^23 magic constant. Returns the integer part and writes the fraction. At exact integers it
+// may return (x-1, frac=1): the same point of a continuous interpolant.
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+constexpr int kMagicBits = 0x4B400000;
+B200_DEV int floor_frac(float x, float& frac) {
+    const float xm = (x - 0.5f) + kMagic;
+    const float x0 = xm - kMagic;
+    frac = x - x0;
+    return __float_as_int(xm) - kMagicBits;
+}
+B200_DEV float lerp_fma(float a, float b, float t) { return fmaf(b - a, t, a); }  // a + (b-a)*t
+
+// ------------------------------------------------------------------------------------------------
+// include/util.gdshaderinc:20-40 (exact)
+// ------------------------------------------------------------------------------------------------
+B200_DEV f2 ray_sphere(f3 center, float radius, f3 ray_origin, f3 ray_dir) {
+    const f3 oc = ray_origin - center;
+    const float b = dot3(oc, ray_dir);
+    const f3 qc = oc - b * ray_dir;
+    float h = radius * radius - dot3(qc, qc);
+    if (h < 0.0f) return f2{1000000.0f, 1000000.0f};
+    h = sqrtf(h);
+    return f2{-b - h, -b + h};
+}
+
+// ------------------------------------------------------------------------------------------------
+// texture fetches in the hot loops (textures are fp32 copies with a one-texel apron, see atmo_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+// texture(u_optical_depth_texture, vec2(u, v)).r — funcs_v2:28; u,v in [0,1] (caller clamps)
+B200_DEV float sample_lut(const float* __restrict__ lut_pad, float u, float v) {
+    float fx, fy;
+    const int xi = floor_frac(u * float(kLut) - 0.5f, fx) + 1;  // padded index of the left texel, 0..256
+    const int yi = floor_frac(v * float(kLut) - 0.5f, fy) + 1;
+    const float* p = lut_pad + yi * kLutPad + xi;
+    const float t00 = __ldg(p), t10 = __ldg(p + 1);
+    const float t01 = __ldg(p + kLutPad), t11 = __ldg(p + kLutPad + 1);
+    return lerp_fma(lerp_fma(t00, t10, fx), lerp_fma(t01, t11, fx), fy);
+}
+
+// texture(u_cloud_coverage_cubemap, d).r — cloud_funcs:45 (seamless bilinear, LOD 0)
+B200_DEV float sample_cube(const float* __restrict__ cube, int res, float x, float y, float z) {
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    int f;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { f = x >= 0.0f ? 0 : 1; ma = ax; sc = x >= 0.0f ? -z : z; tc = -y; }
+    else if (ay >= az)        { f = y >= 0.0f ? 2 : 3; ma = ay; sc = x; tc = y >= 0.0f ? z : -z; }
+    else                      { f = z >= 0.0f ? 4 : 5; ma = az; sc = z >= 0.0f ? x : -x; tc = -y; }
+    const float inv_ma = rcp_approx(ma);
+    // s = 0.5*(sc/ma + 1); xf = s*res - 0.5   (exact op order; the two divisions share one MUFU.RCP)
+    const float s = 0.5f * (div_refined(sc, ma, inv_ma) + 1.0f);
+    const float t = 0.5f * (div_refined(tc, ma, inv_ma) + 1.0f);
+    float fx, fy;
+    int xi = floor_frac(s * float(res) - 0.5f, fx) + 1;
+    int yi = floor_frac(t * float(res) - 0.5f, fy) + 1;
+    xi = min(max(xi, 0), res);  // NaN / rounding guards only: the coordinates are in range by construction
+    yi = min(max(yi, 0), res);
+    const int pr = res + 2;
+    const float* p = cube + (size_t(f) * pr + yi) * pr + xi;
+    const float t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + pr), t11 = __ldg(p + pr + 1);
+    return lerp_fma(lerp_fma(t00, t10, fx), lerp_fma(t01, t11, fx), fy);
+}
+
+// texture(u_cloud_shape_texture, c).r — cloud_funcs:49 (repeat, trilinear, LOD 0)
+B200_DEV float sample_shape(const float* __restrict__ shp, int nx, int ny, int nz, float cx, float cy, float cz) {
+    cx = cx - floorf(cx);  // repeat: wrap to [0,1]
+    cy = cy - floorf(cy);
+    cz = cz - floorf(cz);
+    float fx, fy, fz;
+    int xi = floor_frac(cx * float(nx) - 0.5f, fx) + 1;
+    int yi = floor_frac(cy * float(ny) - 0.5f, fy) + 1;
+    int zi = floor_frac(cz * float(nz) - 0.5f, fz) + 1;
+    xi = min(max(xi, 0), nx);
+    yi = min(max(yi, 0), ny);
+    zi = min(max(zi, 0), nz);
+    const int px = nx + 2, pxy = px * (ny + 2);
+    const float* p = shp + size_t(zi) * pxy + yi * px + xi;
+    const float c00 = lerp_fma(__ldg(p), __ldg(p + 1), fx);
+    const float c10 = lerp_fma(__ldg(p + px), __ldg(p + px + 1), fx);
+    const float c01 = lerp_fma(__ldg(p + pxy), __ldg(p + pxy + 1), fx);
+    const float c11 = lerp_fma(__ldg(p + pxy + px), __ldg(p + pxy + px + 1), fx);
+    return lerp_fma(lerp_fma(c00, c10, fy), lerp_fma(c01, c11, fy), fz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// include/atmosphere_funcs_v2.gdshaderinc:32-101 — N-step in-scatter march against the baked LUT
+// ------------------------------------------------------------------------------------------------
+B200_DEV float4 scatter_v2(const DevConsts& c, f3 o, f3 d, float t_begin, float t_end, float jitter) {
+    const int steps = c.scatter_steps;
+    const f3 C = ld3(c.C), sun = ld3(c.sun_dir);
+    const float step_len = (t_end - t_begin) / float(steps);
+    f3 pos = o + d * t_begin;   // pos0, :57-58 (exact)
+    const f3 dstep = d * step_len;
+    const float ld_scale = c.rho2 * step_len;  // get_atmosphere_density()*u_density*step_len = y^3 * rho^2 * step_len
+    const float k0 = c.neg_coef_log2e[0], k1 = c.neg_coef_log2e[1], k2 = c.neg_coef_log2e[2];
+    float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, view_od = 0.0f;
+
+B200_UNROLL(2)
+    for (int i = 0; i < steps; ++i) {
+        const f3 rel = pos - C;
+        const float d2 = dot3(rel, rel);
+        float inv;
+        const float dist = sqrt_refined(d2, inv);                           // distance(pos, planet_center)
+        const float hr = __saturatef(div_refined(dist - c.R, c.H, c.inv_H)); // height_ratio :17-18 == density's h
+        float mu = fmaf(rel.z, sun.z, fmaf(rel.y, sun.y, rel.x * sun.x)) * inv;  // dot(normalize(pos-C), sun_dir) :19-20
+        mu = fminf(fmaxf(mu, -1.0f), 1.0f);
+        const float sun_od = sample_lut(c.lut_pad, fmaf(0.5f, mu, 0.5f), hr);  // :20,28
+        const float y = 1.0f - hr;                                          // atmosphere_common:14-17
+        const float ld_step = y * y * y * ld_scale;                         // local_density * step_len, :64-65
+        view_od += ld_step;                                                 // :66
+        const float od = sun_od + view_od;
+        const float T0 = ex2_approx(od * k0), T1 = ex2_approx(od * k1), T2 = ex2_approx(od * k2);  // :71-73
+        L0 = fmaf(ld_step, T0, L0);                                         // :75 (coefficient applied after the loop)
+        L1 = fmaf(ld_step, T1, L1);
+        L2 = fmaf(ld_step, T2, L2);
+        pos = pos + dstep;                                                  // :81 (exact)
+    }
+    // alpha: the recurrence a += (1-vt)(1-a), vt = exp(-ld*step) telescopes to 1 - exp(-view_od)  (:78-79)
+    float alpha = 1.0f - ex2_approx(view_od * -1.4426950408889634f);
+    const float r = clampf(fmaf(L0, c.coef[0], c.ambient[0]), 0.0f, 1.0f) * c.modulate[0];  // :91, :98
+    const float g = clampf(fmaf(L1, c.coef[1], c.ambient[1]), 0.0f, 1.0f) * c.modulate[1];
+    const float b = clampf(fmaf(L2, c.coef[2], c.ambient[2]), 0.0f, 1.0f) * c.modulate[2];
+    alpha = clampf(fmaf(jitter, 0.02f, alpha), 0.0f, 0.99f);                                 // :96
+    return make_float4(r, g, b, alpha);
+}
+
+// ------------------------------------------------------------------------------------------------
+// include/atmosphere_funcs_v1.gdshaderinc:15-63 — "lite" model
+// ------------------------------------------------------------------------------------------------
+B200_DEV float4 scatter_v1(const DevConsts& c, f3 o, f3 d, float t_begin, float t_end) {
+    const int steps = c.scatter_steps;
+    const f3 C = ld3(c.C), sun = ld3(c.sun_dir);
+    const float inv_steps = 1.0f / float(steps);
+    const float step_len = (t_end - t_begin) * inv_steps;
+    const f3 stepv = step_len * d;
+    f3 pos = o + d * t_begin;
+    float factor = 1.0f, light_sum = 0.0f;
+B200_UNROLL(2)
+    for (int i = 0; i < steps; ++i) {
+        const f3 rel = pos - C;
+        const float d2 = dot3(rel, rel);
+        float inv;
+        const float dist = sqrt_refined(d2, inv);
+        const float h = __saturatef(div_refined(dist - c.R, c.H, c.inv_H));
+        const float y = 1.0f - h;
+        const float density = y * y * y * c.rho;                       // density applied once in v1 (funcs_v1:33)
+        const float sdot = fmaf(rel.z, sun.z, fmaf(rel.y, sun.y, rel.x * sun.x)) * inv;   // dot(sun_dir, up) :31,35
+        float light = __saturatef(fmaf(1.2f, sdot, 0.5f));
+        light = light * light;                                          // :36
+        light_sum = fmaf(light, inv_steps, light_sum);                  // :38
+        factor *= fmaf(-density, step_len, 1.0f);                       // :39
+        pos = pos + stepv;
+    }
+    const float atmo_factor = 1.0f - factor;
+    const float day_factor = __saturatef(light_sum * c.day_night_scale);
+    float rgb[3];
+    for (int k = 0; k < 3; ++k) {
+        const float night = mixf(c.night0[k], c.night1[k], atmo_factor);
+        const float day = mixf(c.day0[k], c.day1[k], atmo_factor);
+        rgb[k] = mixf(night, day, day_factor);
+    }
+    return make_float4(rgb[0], rgb[1], rgb[2], __saturatef(atmo_factor));
+}
+
+// ------------------------------------------------------------------------------------------------
+// include/cloud_funcs.gdshaderinc
+// ------------------------------------------------------------------------------------------------
+// height_ratio (:36-37, :95-96, :111-112): (|p| - bottom) / (top - bottom)
+B200_DEV float cloud_height_ratio(const DevConsts& c, float len) {
+    return div_refined(len - c.cloud_bottom_h, c.cloud_thickness, c.inv_cloud_thickness);
+}
+
+// get_density_full (:31-68) with |p| and height_ratio already computed; clamped density in [0,1].
+// Exact skip: outside the shell height_curve clamps to 0, so (..)*0*50-20 clamps to exactly 0.
+B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
+    const float a = 2.0f * hr - 1.0f;                                          // height_curve :25-29, exact
+    const float hc = 1.0f - a * a;
+    if (!(hc > 0.0f)) return 0.0f;
+    const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;                         // u_cloud_coverage_rotation * p.xz :43, exact
+    const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
+    float coverage = sample_cube(c.cube_pad, c.cube_res, cpx, p.y, cpz);       // :45
+    coverage = coverage - 0.25f * hr + c.coverage_bias;                        // :46
+    const float tex = sample_shape(c.shape_pad, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
+                                   p.y * c.shape_scale, p.z * c.shape_scale);
+    float shape = mixf(0.5f, tex, c.shape_factor);                             // :48-50
+    if (c.shape_invert) shape = 1.0f - shape;                                  // :57-59
+    // detail = 0.5 (CLOUDS_ALWAYS_LOW_QUALITY, main:49) => 0.2*detail = 0.1 (same fp32 product)
+    float density = (shape - 0.2f * 0.5f + mixf(-1.2f, 1.5f, coverage)) * hc;  // :61
+    density = density * 50.0f - 20.0f;                                         // :62
+    return __saturatef(density);                                               // :64
+}
+
+// get_light_raymarched (:104-151)
+B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0) {
+    float step_len = c.light_reach * (1.0f / 6.0f);   // reach * inv_steps
+    float transm = 1.0f;                               // 1 - alpha
+B200_UNROLL(1)
+    for (int i = 0; i < 6; ++i) {
+        const float t = float(i) * step_len;
+        const f3 p = mk3(pos0.x + t * sun.x, pos0.y + t * sun.y, pos0.z + t * sun.z);  // :129, exact
+        float inv;
+        const float len = sqrt_refined(dot3(p, p), inv);
+        const float dens = cloud_density(c, p, cloud_height_ratio(c, len));
+        if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.density_scale) * -1.4426950408889634f);  // :138-142
+        step_len *= 1.2f;                                                                                   // :143
+    }
+    const float alpha = 1.0f - transm;
+    return mixf(1.0f, hr0 * 0.2f, alpha);              // :146-150
+}
+
+// raymarch_cloud (:175-247) in model space; returns (total_light, alpha)
+template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, float t_begin, float t_end, float jitter, f3 sun) {
+    const int steps = c.cloud_steps;
+    // march-length cap (:186-204), exact
+    const float max_d = mixf(c.march_ground, c.march_space, smoothstepf(c.march_hmin, c.march_hmax, sqrtf(dot3(o, o))));
+    t_end = t_begin + fminf(t_end - t_begin, max_d);
+    const float inv_steps = 1.0f / float(steps);
+    const float step_len = (t_end - t_begin) * inv_steps;
+    f3 pos = o + jitter * step_len * d + d * t_begin;  // :213, exact
+    const f3 dstep = d * step_len;
+
+    // loop invariant: max(pow(dot(ray_dir, sun_dir), 16), 0) (:98-101; a non-positive base gives 0)
+    float sunpeek = 0.0f;
+    if (LIGHT == B200ATMO_LIGHT_CHEAP) {
+        const float dp = dot3(d, sun);
+        if (dp > 0.0f) {
+            const float p2 = dp * dp, p4 = p2 * p2, p8 = p4 * p4;
+            sunpeek = p8 * p8;
+        }
+    }
+    const float k = step_len * c.density_scale;
+    float T_clamped = 1.0f;  // total_transmittance (:222-223)
+    float T_alpha = 1.0f;    // 1 - alpha (:228 telescopes to a product of transmittances)
+    float total_light = 0.0f;
+B200_UNROLL(1)
+    for (int i = 0; i < steps; ++i) {
+        float inv;
+        const float len = sqrt_refined(dot3(pos, pos), inv);
+        const float hr = cloud_height_ratio(c, len);
+        const float dens01 = cloud_density(c, pos, hr);
+        if (dens01 > 0.0f) {  // density == 0 => transmittance 1, no light added, alpha unchanged: exact skip
+            float light;      // get_light (:153-167)
+            if (LIGHT == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched(c, pos, sun, hr);
+            else light = fmaf(sunpeek, T_alpha, hr);                                         // :95-101
+            const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);  // dot(normalize(pos), -sun)
+            const float st = __saturatef((sdot + 0.3f) * (1.0f / 0.6f));                     // smoothstep(-0.3, 0.3, .) :87
+            const float shadow = st * st * fmaf(-2.0f, st, 3.0f);
+            light *= fmaf(shadow, -0.998f, 1.0f);                                             // mix(1, 0.002, shadow) :164
+            const float dens_step = dens01 * k;                                               // density*scale*step_len
+            const float tr = ex2_approx(dens_step * -1.4426950408889634f);                    // :221
+            T_clamped = fmaxf(T_clamped * tr, 0.005f);                                        // :222-223
+            total_light = fmaf(light * dens_step, T_clamped, total_light);                    // :226
+            T_alpha *= tr;                                                                    // :228
+        }
+        pos = pos + dstep;  // :236, exact
+    }
+    return f2{total_light, 1.0f - T_alpha};
+}
+
+// render_clouds (:249-324). Set-up and visibility test exact.
+template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px, f3 o, f3 d, float linear_depth, float jitter) {
+    const f3 C = ld3(c.C);
+    const f2 rs_top = ray_sphere(C, c.cloud_top_h, o, d);
+    if (rs_top.x == rs_top.y) return;
+    const f2 rs_bottom = ray_sphere(C, c.cloud_bottom_h, o, d);
+    const float t0 = fmaxf(rs_top.x, 0.0f);
+    const float t1 = fminf(rs_top.y, linear_depth);
+    if (!(t0 < linear_depth && (linear_depth > rs_bottom.y || rs_bottom.x > 0.0f))) return;  // :273-278
+    float om[4], dm[4];
+    mat4_mul(c.v2m, o.x, o.y, o.z, 1.0f, om);  // :286-287
+    mat4_mul(c.v2m, d.x, d.y, d.z, 0.0f, dm);
+    const f2 rr = raymarch_cloud<LIGHT>(c, mk3(om[0], om[1], om[2]), mk3(dm[0], dm[1], dm[2]), t0, t1, jitter,
+                                        ld3(c.sun_dir_model));
+    const float cl = rr.x, ca = rr.y;
+    // blend_colors(self = atmosphere, over = cloud), util:61-69
+    const float sa = 1.0f - ca;
+    const float a = px.w * sa + ca;
+    float br = 0.f, bg = 0.f, bb = 0.f, ba = 0.f;
+    if (a != 0.0f) {
+        br = (px.x * px.w * sa + cl * ca) / a;
+        bg = (px.y * px.w * sa + cl * ca) / a;
+        bb = (px.z * px.w * sa + cl * ca) / a;
+        ba = a;
+    }
+    const float ar = px.x + cl * ca, ag = px.y + cl * ca, ab = px.z + cl * ca, aa = fmaxf(px.w, ca);  // :308-310
+    px.x = mixf(br, ar, c.cloud_blend);  // :318
+    px.y = mixf(bg, ag, c.cloud_blend);
+    px.z = mixf(bb, ab, c.cloud_blend);
+    px.w = mixf(ba, aa, c.cloud_blend);
+}
+
+// ------------------------------------------------------------------------------------------------
+// include/planet_atmosphere_main.gdshaderinc:144-196 — one fragment, ray already generated
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int LIGHT> B200_DEV bool shade_ray(const DevConsts& c, f3 o, f3 d, float linear_depth, float jitter, float4& out) {
+    const f3 C = ld3(c.C);
+    const f2 rs_atmo = ray_sphere(C, c.atmo_radius, o, d);
+    if (rs_atmo.x == rs_atmo.y) {  // miss (or tangent): discard, :150,191-196
+        out = make_float4(0.f, 0.f, 0.f, 0.f);
+        return true;
+    }
+    const float t_begin = fmaxf(rs_atmo.x, 0.0f);
+    float t_end = fmaxf(rs_atmo.y, 0.0f);
+    const f2 rs_ground = ray_sphere(C, c.R, o, d);
+    float gd = 10000000.0f;
+    if (rs_ground.x != rs_ground.y) gd = rs_ground.x;
+    linear_depth = mixf(linear_depth, gd, c.sphere_depth_factor);  // :160
+    t_end = fminf(t_end, linear_depth);                            // :162
+    if (MODEL == B200ATMO_SCATTER_V1) out = scatter_v1(c, o, d, t_begin, t_end);
+    else out = scatter_v2(c, o, d, t_begin, t_end, jitter);
+    if (LIGHT != B200ATMO_LIGHT_NONE) render_clouds<LIGHT>(c, out, o, d, linear_depth, jitter);
+    return false;
+}
+
+// main:128-142 — ray generation from the depth texture (exact arithmetic, shader op order)
+B200_DEV void make_ray(const DevConsts& c, int x, int y, float nonlinear_depth, f3& o, f3& d, float& linear_depth, float& jitter) {
+    const float su = (float(x) + 0.5f) / float(c.fw), sv = (float(y) + 0.5f) / float(c.fh);  // SCREEN_UV
+    float vc[4], wc[4];
+    mat4_mul(c.inv_proj, su * 2.0f - 1.0f, sv * 2.0f - 1.0f, nonlinear_depth, 1.0f, vc);  // :130-131
+    mat4_mul(c.inv_view_ray, vc[0], vc[1], vc[2], vc[3], wc);                             // :134
+    const f3 pos_world = mk3(wc[0] / wc[3], wc[1] / wc[3], wc[2] / wc[3]);                // :135
+    const f3 dc = ld3(c.cam_pos_world) - pos_world;
+    linear_depth = sqrtf(dot3(dc, dc));                                                   // :138
+    o = mk3(0.f, 0.f, 0.f);                                                               // :141
+    const f3 v = mk3(vc[0], vc[1], vc[2]) - o;
+    const float l = sqrtf(dot3(v, v));
+    d = mk3(v.x / l, v.y / l, v.z / l);                                                   // :142
+    jitter = 0.0f;
+    if (c.blue_noise) jitter = float(c.blue_noise[(y & (c.bn_h - 1)) * c.bn_w + (x & (c.bn_w - 1))]) / 255.0f;  // :168-169
+}
+
+}  // namespace b200atmo

@@ -1,0 +1,81 @@
+// Internal interface between the C-ABI (atmo_capi.cu) and the kernels (atmo_kernels.cu).
+// Not installed; the public surface is include/b200atmo.h.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200atmo.h"
+
+namespace b200atmo {
+
+constexpr int kLut = B200ATMO_LUT_SIZE;      // 256
+constexpr int kLutPad = kLut + 2;            // clamp-to-edge apron of one texel on every side
+
+// Everything a render kernel needs, passed by value as a __grid_constant__ kernel parameter.
+// Host code (atmo_consts.h) fills it with plain fp32 arithmetic in the shader's op order, no FMA
+// contraction, so per-frame constants are bit-identical to what the shader computes per fragment.
+struct DevConsts {
+    // --- planet / atmosphere (planet_common, atmosphere_common) ---
+    float R, H, rho, atmo_radius;
+    float sphere_depth_factor;
+    float C[3];            // v_planet_center_viewspace
+    float sun_dir[3];      // normalize(v_sun_center_viewspace - v_planet_center_viewspace), main:164
+    // --- scattering v2 ---
+    float coef[3];         // scattering_coefficients, funcs_v2:47-51
+    float neg_coef_log2e[3];
+    float ambient[3], modulate[3];
+    float inv_H;           // 1/H, correctly rounded
+    float rho2;            // rho*rho (density is applied twice, funcs_v2:65)
+    const float* lut_pad;  // [kLutPad][kLutPad] fp32
+    // --- scattering v1 ---
+    float day0[3], day1[3], night0[3], night1[3];
+    float day_night_scale;
+    // --- clouds ---
+    float cloud_bottom_h, cloud_top_h;   // R + u_cloud_bottom*H, R + u_cloud_top*H  (cloud_funcs:260-261)
+    float cloud_thickness;               // top - bottom
+    float inv_cloud_thickness;           // 1/(top-bottom), correctly rounded
+    float density_scale, cloud_blend, coverage_bias, shape_factor, shape_scale;
+    int shape_invert;                    // u_cloud_shape_invert == 1.0
+    float rot[4];                        // mat2 column-major
+    float v2m[16];                       // view_to_model = u_world_to_model_matrix * inv_view (cloud_funcs:285), column-major
+    float sun_dir_model[3];              // (view_to_model * vec4(sun_dir, 0)).xyz, cloud_funcs:288
+    float march_space, march_ground;     // cloud_funcs:186-190
+    float march_hmin, march_hmax;        // cloud_funcs:191-192
+    float light_reach;                   // (top-bottom)*0.15, cloud_funcs:108
+    const float* cube_pad;               // [6][res+2][res+2] fp32 (= u8/255), seamless apron
+    int cube_res;
+    const float* shape_pad;              // [nz+2][ny+2][nx+2] fp32 (= u8/255), repeat apron
+    int shape_nx, shape_ny, shape_nz;
+    // --- variant ---
+    int scatter_steps, cloud_steps;
+    // --- frame front-end (unused by the ray-batch kernels) ---
+    float inv_proj[16], inv_view_ray[16];  // inv_view_ray: INV_VIEW_MATRIX after the DOUBLE_PRECISION fix-up (main:118-125)
+    float cam_pos_world[3];                // (inv_view * (0,0,0,1)).xyz, main:136
+    const uint8_t* blue_noise;
+    int bn_w, bn_h;
+    int fw, fh, row_begin, row_end;
+};
+
+struct RayIO {
+    const void* origin_depth;  // float4[n]   ray batch in
+    const void* dir_jitter;    // float4[n]
+    const float* depth;        // float[w*h]  frame in
+    void* rgba;                // float4[...] out
+    uint8_t* discard;          // nullable
+    void* out_origin_depth;    // make_rays only
+    void* out_dir_jitter;
+    size_t n;
+};
+
+#ifdef __CUDACC__
+// kernels (atmo_kernels.cu)
+cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, cudaStream_t s);
+cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, cudaStream_t s);
+cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, cudaStream_t s);
+cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
+cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
+cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
+#endif
+
+}  // namespace b200atmo

@@ -1,0 +1,217 @@
+// sm_100a kernels of the atmosphere hot path + their launchers. Compile with -fmad=false (see the
+// numeric policy in atmo_device.cuh).
+#include <cuda_runtime.h>
+
+#include "atmo_device.cuh"
+
+namespace b200atmo {
+
+// ------------------------------------------------------------------------------------------------
+// optical_depth.gdshader:17-69 — LUT bake, exact arithmetic => bit-identical to the shader's floats.
+// One thread per texel; also writes the clamp-to-edge padded copy the render kernels sample.
+// Replaces the SubViewport render + RGBA8 bit-pack + FORMAT_RF reinterpretation
+// (optical_depth.gdshader:33-43, optical_depth_baker.gd:74-85): that round trip is lossless.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bake_lut_kernel(float R, float H, float rho, float* __restrict__ lut,
+                                                        float* __restrict__ lut_pad) {
+    const int i = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const float uvx = (float(i) + 0.5f) / float(kLut);  // canvas UV of the texel centre
+    const float uvy = (float(j) + 0.5f) / float(kLut);
+    const float dir_y = 2.0f * uvx - 1.0f;               // :48-51
+    const float dir_x = sqrtf(1.0f - dir_y * dir_y);
+    const float pos_y = R + H * uvy;                      // :53-55
+    const f2 rs = ray_sphere(mk3(0.f, 0.f, 0.f), R + H, mk3(0.0f, pos_y, 0.0f), mk3(dir_x, dir_y, 0.0f));
+    const float ray_len = rs.y - fmaxf(rs.x, 0.0f);       // :63
+    // get_optical_depth (:17-31), 64-step left Riemann sum
+    const float step_len = ray_len / 64.0f;
+    float od = 0.0f;
+    for (int s = 0; s < 64; ++s) {
+        const float px = 0.0f + dir_x * step_len * float(s);
+        const float py = pos_y + dir_y * step_len * float(s);
+        const float d = sqrtf(px * px + py * py);
+        const float sd = d - R;                           // get_atmosphere_density (atmosphere_common:12-24)
+        const float h = clampf(sd / H, 0.0f, 1.0f);
+        const float y = 1.0f - h;
+        const float density = y * y * y * rho;
+        od += density * step_len * rho;
+    }
+    lut[j * kLut + i] = od;
+    // padded copy: pad[j+1][i+1]; aprons replicate the edge (repeat_disable = clamp to edge)
+    const int xs = (i == 0) ? 0 : i + 1, xe = (i == kLut - 1) ? kLutPad - 1 : i + 1;
+    const int ys = (j == 0) ? 0 : j + 1, ye = (j == kLut - 1) ? kLutPad - 1 : j + 1;
+    for (int y2 = ys; y2 <= ye; ++y2)
+        for (int x2 = xs; x2 <= xe; ++x2) lut_pad[y2 * kLutPad + x2] = od;
+}
+
+cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, cudaStream_t s) {
+    bake_lut_kernel<<<dim3(kLut / 16, kLut / 16), 256, 0, s>>>(R, H, rho, d_lut, d_lut_pad);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Seamless cube layout (integer, bit-exact with the oracle's cube_build_padded): per face a
+// (res+2)^2 image whose one-texel apron holds the texel adjacent across the cube edge; the corner
+// apron is the rounded mean of the three texels meeting at that cube corner. Bilinear filtering
+// inside the padded face is then continuous across faces (the Vulkan seamless-cube rule).
+// Face order +X,-X,+Y,-Y,+Z,-Z and (sc,tc) tables agree with noise_cubemap.gd:110-128.
+// ------------------------------------------------------------------------------------------------
+__constant__ int kFaceN[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+__constant__ int kFaceS[6][3] = {{0, 0, -1}, {0, 0, 1}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {-1, 0, 0}};
+__constant__ int kFaceT[6][3] = {{0, -1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {0, -1, 0}, {0, -1, 0}};
+
+// texel (i,j) of face f where at most one of i,j lies one step outside [0,res): fold over the cube edge
+__device__ int cube_edge_texel(const uint8_t* faces, int res, int f, int i, int j) {
+    const bool io = (i < 0 || i >= res), jo = (j < 0 || j >= res);
+    if (!io && !jo) return faces[(size_t(f) * res + j) * res + i];
+    const int sc = 2 * i + 1 - res, tc = 2 * j + 1 - res;  // doubled texel units, face plane at +-res
+    int s = sc, t = tc;
+    const int nrm = res - 1;
+    if (io) s = sc > 0 ? res : -res;
+    else t = tc > 0 ? res : -res;
+    int P[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) P[k] = kFaceN[f][k] * nrm + kFaceS[f][k] * s + kFaceT[f][k] * t;
+    int g;
+    if (abs(P[0]) == res) g = P[0] > 0 ? 0 : 1;
+    else if (abs(P[1]) == res) g = P[1] > 0 ? 2 : 3;
+    else g = P[2] > 0 ? 4 : 5;
+    const int gs = kFaceS[g][0] * P[0] + kFaceS[g][1] * P[1] + kFaceS[g][2] * P[2];
+    const int gt = kFaceT[g][0] * P[0] + kFaceT[g][1] * P[1] + kFaceT[g][2] * P[2];
+    const int gi = (gs + res - 1) / 2, gj = (gt + res - 1) / 2;
+    return faces[(size_t(g) * res + gj) * res + gi];
+}
+
+__global__ void cube_pad_kernel(const uint8_t* __restrict__ faces, int res, uint8_t* __restrict__ padded,
+                                float* __restrict__ padded_f32) {
+    const int pr = res + 2;
+    const size_t total = size_t(6) * pr * pr;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int f = int(idx / (size_t(pr) * pr));
+        const int rem = int(idx % (size_t(pr) * pr));
+        const int j = rem / pr - 1, i = rem % pr - 1;
+        const bool io = (i < 0 || i >= res), jo = (j < 0 || j >= res);
+        int v;
+        if (io && jo) {
+            const int ii = i < 0 ? 0 : res - 1, jj = j < 0 ? 0 : res - 1;
+            const int a = cube_edge_texel(faces, res, f, ii, j);   // apron next to the corner, same row
+            const int b = cube_edge_texel(faces, res, f, i, jj);   // apron next to the corner, same column
+            const int c = cube_edge_texel(faces, res, f, ii, jj);  // the face's own corner texel
+            v = (2 * (a + b + c) + 3) / 6;
+        } else {
+            v = cube_edge_texel(faces, res, f, i, j);
+        }
+        padded[idx] = uint8_t(v);
+        padded_f32[idx] = float(v) / 255.0f;  // IEEE division: the value a UNORM8 fetch returns
+    }
+}
+
+cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, cudaStream_t s) {
+    const size_t total = size_t(6) * (res + 2) * (res + 2);
+    const int blocks = int((total + 255) / 256);
+    cube_pad_kernel<<<blocks > 4096 ? 4096 : blocks, 256, 0, s>>>(d_faces, res, d_padded, d_padded_f32);
+    return cudaGetLastError();
+}
+
+// 3D shape: repeat-padded fp32 copy [nz+2][ny+2][nx+2], padded[z+1][y+1][x+1] = texel(x mod nx, ..)/255
+__global__ void shape_pad_kernel(const uint8_t* __restrict__ src, int nx, int ny, int nz, float* __restrict__ dst) {
+    const int px = nx + 2, py = ny + 2, pz = nz + 2;
+    const size_t total = size_t(px) * py * pz;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int x = int(idx % px), y = int((idx / px) % py), z = int(idx / (size_t(px) * py));
+        const int sx = (x - 1 + nx) % nx, sy = (y - 1 + ny) % ny, sz = (z - 1 + nz) % nz;
+        dst[idx] = float(src[(size_t(sz) * ny + sy) * nx + sx]) / 255.0f;
+    }
+}
+
+cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, cudaStream_t s) {
+    const size_t total = size_t(nx + 2) * (ny + 2) * (nz + 2);
+    const int blocks = int((total + 255) / 256);
+    shape_pad_kernel<<<blocks > 8192 ? 8192 : blocks, 256, 0, s>>>(d_src, nx, ny, nz, d_dst);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// render kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlock = 128;
+
+// Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
+template <int MODEL, int LIGHT>
+__global__ void __launch_bounds__(kBlock) render_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+    const size_t i = blockIdx.x * size_t(kBlock) + threadIdx.x;
+    if (i >= io.n) return;
+    const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
+    const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
+    float4 out;
+    const bool disc = shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
+    __stcs(static_cast<float4*>(io.rgba) + i, out);
+    if (io.discard) io.discard[i] = disc ? 1 : 0;
+}
+
+// Frame: a warp covers an 8x4 pixel tile (coherent LUT / texture footprints, full 128 B store
+// segments per tile row), a block of 4 warps a 16x8 tile.
+template <int MODEL, int LIGHT>
+__global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = c.row_begin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= c.fw || y >= c.row_end) return;
+    const size_t i = size_t(y) * c.fw + x;
+    f3 o, d;
+    float linear_depth, jitter;
+    make_ray(c, x, y, __ldcs(io.depth + i), o, d, linear_depth, jitter);
+    float4 out;
+    const bool disc = shade_ray<MODEL, LIGHT>(c, o, d, linear_depth, jitter, out);
+    __stcs(static_cast<float4*>(io.rgba) + i, out);
+    if (io.discard) io.discard[i] = disc ? 1 : 0;
+}
+
+// Frame front-end only: depth buffer -> SoA rays for the batch API.
+__global__ void __launch_bounds__(kBlock) make_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+    const size_t i = blockIdx.x * size_t(kBlock) + threadIdx.x;
+    if (i >= io.n) return;
+    const int x = int(i % size_t(c.fw)), y = int(i / size_t(c.fw));
+    f3 o, d;
+    float linear_depth, jitter;
+    make_ray(c, x, y, io.depth[i], o, d, linear_depth, jitter);
+    static_cast<float4*>(io.out_origin_depth)[i] = make_float4(o.x, o.y, o.z, linear_depth);
+    static_cast<float4*>(io.out_dir_jitter)[i] = make_float4(d.x, d.y, d.z, jitter);
+}
+
+#define B200ATMO_DISPATCH(KERNEL, GRID, ...)                                                               \
+    do {                                                                                                   \
+        if (scatter_model == B200ATMO_SCATTER_V1) {                                                         \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);       \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<1, 2><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                         \
+        } else {                                                                                           \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);       \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<0, 2><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                         \
+        }                                                                                                  \
+    } while (0)
+
+cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+    if (io.n == 0) return cudaSuccess;
+    const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
+    B200ATMO_DISPATCH(render_rays_kernel, grid, c, io);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+    const int rows = c.row_end - c.row_begin;
+    if (rows <= 0 || c.fw <= 0) return cudaSuccess;
+    const dim3 grid((c.fw + 15) / 16, (rows + 7) / 8);
+    B200ATMO_DISPATCH(render_frame_kernel, grid, c, io);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s) {
+    if (io.n == 0) return cudaSuccess;
+    const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
+    make_rays_kernel<<<grid, kBlock, 0, s>>>(c, io);
+    return cudaGetLastError();
+}
+
+}  // namespace b200atmo

@@ -1,0 +1,206 @@
+/*
+ * b200atmo.h — C-ABI of the B200-native batched atmosphere raymarcher.
+ *
+ * Drop-in boundary for ONE hot path of Zylann/godot_atmosphere_shader: the per-pixel integration of
+ *   addons/zylann.atmosphere/shaders/include/planet_atmosphere_main.gdshaderinc:106-197   (atmosphere_fragment)
+ *   addons/zylann.atmosphere/shaders/include/atmosphere_funcs_v2.gdshaderinc:14-101       (LUT fetch + in-scatter march)
+ *   addons/zylann.atmosphere/shaders/include/atmosphere_funcs_v1.gdshaderinc:15-63        (v1 "lite" model)
+ *   addons/zylann.atmosphere/shaders/include/cloud_funcs.gdshaderinc:25-324               (cloud march + lighting)
+ *   addons/zylann.atmosphere/shaders/optical_depth.gdshader:17-69                         (LUT bake)
+ *
+ * The reference has no FFI: its "operator interface" is Godot's ShaderMaterial uniform set plus the
+ * spatial-shader built-ins, driven by the PlanetAtmosphere GDScript node
+ * (addons/zylann.atmosphere/planet_atmosphere.gd). Each entry point below names the reference
+ * interface it replaces. INTEGRATION.md shows the GDExtension-side binding.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in signatures; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - all matrices are COLUMN-MAJOR float[16] (GLSL mat4: m[col*4+row]), vectors are float[3]
+ *   - colours are LINEAR (Godot converts `source_color` uniforms sRGB->linear before upload; do the same)
+ *   - `d_*` pointers are device memory owned by the caller, `h_*` pointers are host memory owned by the caller
+ *   - the context owns the optical-depth LUT and all textures; one context per device; not thread-safe
+ *     (the reference only ever runs on Godot's main thread, planet_atmosphere.gd:285)
+ *   - every call returns 0 on success or a negative B200ATMO_E_* code; b200atmo_last_error() gives the text
+ *   - there is NO CPU fallback: without a CUDA device b200atmo_create() fails with B200ATMO_E_CUDA
+ */
+#ifndef B200ATMO_H
+#define B200ATMO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ATMO_VERSION 1
+
+enum {
+    B200ATMO_OK = 0,
+    B200ATMO_E_INVALID = -1, /* bad argument (null pointer, negative size, unsupported variant ...) */
+    B200ATMO_E_CUDA = -2,    /* CUDA runtime error (text in last_error) */
+    B200ATMO_E_NOMEM = -3,   /* host or device allocation failed */
+    B200ATMO_E_STATE = -4    /* call sequence error */
+};
+
+/* Scattering model = which include the entry shader pulls in (planet_atmosphere_main.gdshaderinc:27-31). */
+enum {
+    B200ATMO_SCATTER_V2 = 0,  /* atmosphere_funcs_v2.gdshaderinc  (planet_atmosphere_*.gdshader)    */
+    B200ATMO_SCATTER_V1 = 1   /* atmosphere_funcs_v1.gdshaderinc  (planet_atmosphere_v1_*.gdshader) */
+};
+
+/* Cloud lighting = CLOUDS_ENABLED / CLOUDS_RAYMARCHED_LIGHTING (planet_atmosphere_main.gdshaderinc:33,50). */
+enum {
+    B200ATMO_LIGHT_NONE = 0,       /* clouds disabled               (*_no_clouds.gdshader)         */
+    B200ATMO_LIGHT_CHEAP = 1,      /* get_light_cheap               (*_clouds[_high].gdshader)      */
+    B200ATMO_LIGHT_RAYMARCHED = 2  /* get_light_raymarched, 6 steps (*_clouds_high_rm.gdshader)     */
+};
+
+/*
+ * The shader uniform set. Field name = uniform name without the `u_` prefix.
+ * Defaults are the shader-source defaults; b200atmo_default_params() fills them.
+ */
+typedef struct B200AtmoParams {
+    /* planet_common.gdshaderinc:4-6 */
+    float planet_radius;            /* u_planet_radius = 1.0 */
+    float atmosphere_height;        /* u_atmosphere_height = 0.1 */
+    float sun_position[3];          /* u_sun_position (world space); only the frame API reads it */
+    /* atmosphere_common.gdshaderinc:10 */
+    float density;                  /* u_density = 0.2 (affects the LUT) */
+    /* atmosphere_funcs_v2.gdshaderinc:8-11 */
+    float scattering_strength;      /* 20.0 */
+    float scattering_wavelengths[3];/* (700, 530, 440) */
+    float atmosphere_modulate[3];   /* (1,1,1), linear */
+    float atmosphere_ambient_color[3]; /* (0,0,0.002), linear */
+    /* planet_atmosphere_main.gdshaderinc:55,60 */
+    float clip_mode;                /* u_clip_mode: vertex stage only; carried for surface parity, unused by kernels */
+    float sphere_depth_factor;      /* 0.0 */
+    /* cloud_funcs.gdshaderinc:5-16 */
+    float cloud_density_scale;      /* 50.0 */
+    float cloud_bottom;             /* 0.2 */
+    float cloud_top;                /* 0.5 */
+    float cloud_blend;              /* 0.5 */
+    float cloud_shape_invert;       /* 0.0 (tested == 1.0) */
+    float cloud_coverage_bias;      /* 0.0 */
+    float cloud_shape_factor;       /* 0.8 */
+    float cloud_shape_scale;        /* 1.0 */
+    float cloud_coverage_rotation[4]; /* mat2, column-major: (c0.x, c0.y, c1.x, c1.y); identity by default */
+    float world_to_model[16];       /* u_world_to_model_matrix; identity by default */
+    /* atmosphere_funcs_v1.gdshaderinc:7-11 (only read when scatter model is V1) */
+    float day_color0[4];            /* (0.5,0.8,1,1) linear */
+    float day_color1[4];
+    float night_color0[4];          /* (0.2,0.4,0.8,1) linear */
+    float night_color1[4];
+    float day_night_transition_scale; /* 2.0 */
+} B200AtmoParams;
+
+/*
+ * Per-frame constants for the RAY-BATCH API: the two varyings written by atmosphere_vertex
+ * (planet_atmosphere_main.gdshaderinc:101-103) plus INV_VIEW_MATRIX (needed by render_clouds,
+ * cloud_funcs.gdshaderinc:285). Rays are expressed in the same (view) space as these.
+ */
+typedef struct B200AtmoFrame {
+    float planet_center_view[3];    /* v_planet_center_viewspace */
+    float sun_center_view[3];       /* v_sun_center_viewspace */
+    float inv_view[16];             /* INV_VIEW_MATRIX */
+} B200AtmoFrame;
+
+/*
+ * Camera block for the FRAME API = the spatial-shader built-ins consumed by vertex()/fragment()
+ * (planet_atmosphere_no_clouds.gdshader:13-26).
+ */
+typedef struct B200AtmoCamera {
+    float inv_projection[16];       /* INV_PROJECTION_MATRIX (Vulkan 0..1 depth, as Godot passes it) */
+    float inv_view[16];             /* INV_VIEW_MATRIX */
+    float view[16];                 /* VIEW_MATRIX */
+    float model[16];                /* MODEL_MATRIX of the PlanetAtmosphere node */
+    int32_t double_precision;       /* != 0: DOUBLE_PRECISION workaround, negate inv_view origin (main:118-125) */
+    int32_t reserved;
+} B200AtmoCamera;
+
+typedef struct b200atmo_ctx b200atmo_ctx;
+
+/* ---- lifetime / errors ---------------------------------------------------------------------- */
+int b200atmo_version(void);
+size_t b200atmo_sizeof_params(void);   /* ABI self-check for bindings */
+size_t b200atmo_sizeof_frame(void);
+size_t b200atmo_sizeof_camera(void);
+/* Replaces: ShaderMaterial.new() + material.shader = ... (planet_atmosphere.gd:84-108). */
+int b200atmo_create(int cuda_device, b200atmo_ctx** out);
+void b200atmo_destroy(b200atmo_ctx* ctx);
+/* Replaces: push_error/push_warning strings (planet_atmosphere.gd:165,171). ctx may be NULL (create errors). */
+const char* b200atmo_last_error(const b200atmo_ctx* ctx);
+
+/* ---- uniforms -------------------------------------------------------------------------------- */
+void b200atmo_default_params(B200AtmoParams* out);
+/* Replaces: material.set_shader_parameter(...) for every scalar/vector/matrix uniform
+ * (planet_atmosphere.gd:175-180, 211-218, 230-253, 328-341). A change of planet_radius,
+ * atmosphere_height or density marks the LUT stale exactly like _request_bake_optical_depth
+ * (planet_atmosphere.gd:144-150, 217-218, 237-238, 252-253). */
+int b200atmo_set_params(b200atmo_ctx* ctx, const B200AtmoParams* p);
+int b200atmo_get_params(const b200atmo_ctx* ctx, B200AtmoParams* out);
+/* Replaces: custom_shader selection, i.e. the compile-time #defines of the entry shaders
+ * (shaders/planet_atmosphere_*.gdshader:4-7). scatter_steps >= 1; cloud_steps >= 1 unless light_mode is NONE. */
+int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps, int cloud_steps, int light_mode);
+
+/* ---- textures (host -> device; the context keeps its own device copy) -------------------------- */
+/* u_blue_noise_texture (planet_atmosphere_main.gdshaderinc:63,168-169): w x h, 8-bit, nearest, repeat.
+ * Sizes must be powers of two in [1, 4096] for the `& 0xff`-style wrap; the reference uses 256 x 256. */
+int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w, int h);
+/* u_cloud_shape_texture (cloud_funcs.gdshaderinc:10,48-50): nx*ny*nz 8-bit, x fastest; trilinear, repeat. */
+int b200atmo_upload_shape3d(b200atmo_ctx* ctx, const uint8_t* h_texels, int nx, int ny, int nz);
+/* u_cloud_coverage_cubemap (cloud_funcs.gdshaderinc:15,43-45): 6 faces of res*res 8-bit, face order
+ * +X,-X,+Y,-Y,+Z,-Z (noise_cubemap.gd:116-128), row 0 = top. Seamless bilinear, LOD 0. */
+int b200atmo_upload_coverage_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res);
+
+/* ---- optical-depth LUT (replaces OpticalDepthBaker, optical_depth_baker.gd:37-85) -------------- */
+#define B200ATMO_LUT_SIZE 256
+int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream);
+int b200atmo_download_lut(b200atmo_ctx* ctx, float* h_lut256x256);    /* bakes first if stale; synchronises */
+/* Debug/parity: device texture layouts as seen by the kernels. */
+int b200atmo_download_cube_padded(b200atmo_ctx* ctx, uint8_t* h_out, size_t cap, int* out_res);
+
+/* ---- RAY-BATCH API (device buffers, asynchronous on `stream`) ---------------------------------- */
+/*
+ * One ray = one fragment invocation. SoA of float4:
+ *   d_origin_depth[i] = (ray_origin.xyz [view space], linear_depth)   (main:138,141; depth BEFORE the sphere mix :160)
+ *   d_dir_jitter[i]   = (ray_dir.xyz [normalised],    jitter)         (main:142,169)
+ *   d_rgba[i]         = (ALBEDO.rgb, ALPHA); (0,0,0,0) when discarded
+ *   d_discard[i]      = 1 if `discard` (main:191-196) else 0; may be NULL
+ * Replaces: one draw of the atmosphere mesh (fragment stage), planet_atmosphere_*.gdshader fragment().
+ */
+int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
+                         const float* d_origin_depth, const float* d_dir_jitter, size_t n_rays,
+                         float* d_rgba, uint8_t* d_discard, void* stream);
+/* Same call with HOST buffers: H2D of the rays, render, D2H of the result; synchronous. */
+int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
+                              const float* h_origin_depth, const float* h_dir_jitter, size_t n_rays,
+                              float* h_rgba, uint8_t* h_discard);
+
+/* ---- FRAME API --------------------------------------------------------------------------------- */
+/*
+ * Runs atmosphere_fragment for every pixel of a w x h target (rows [row_begin, row_end) only — the
+ * screen-tile shard used for multi-GPU): depth fetch, ray generation (main:128-142), the varyings of
+ * atmosphere_vertex (main:101-103) from camera->view/model and params.sun_position, blue-noise fetch.
+ *   d_depth : w*h floats, the depth texture (non-linear, as sampled by `texture(depth_texture, uv).x`), row 0 = top
+ *   d_rgba  : w*h float4, only rows [row_begin,row_end) are written
+ *   d_discard: w*h bytes or NULL
+ */
+int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth,
+                          int w, int h, int row_begin, int row_end,
+                          float* d_rgba, uint8_t* d_discard, void* stream);
+/* Frame front-end only (main:101-103,128-142): depth buffer -> the SoA ray buffers of the ray-batch API and
+ * the frame constants that go with them (frame_out may be NULL). */
+int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                       float* d_origin_depth, float* d_dir_jitter, B200AtmoFrame* frame_out, void* stream);
+/* HOST-buffer variant (the e2e path): H2D depth, render, D2H rgba (+discard); synchronous. */
+int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
+                               int w, int h, float* h_rgba, uint8_t* h_discard);
+
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */
+uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ATMO_H */

@@ -1,0 +1,98 @@
+// TEST INFRASTRUCTURE ONLY — never loaded by the product.
+// Compiles the product's device functions (csrc/atmo_device.cuh) as plain host C++ so the logic of the
+// kernels can be exercised without a GPU (`-m "not gpu"` tests). MUFU approximations are replaced by
+// libm (ex2 -> exp2f, rsqrt -> 1/sqrtf, rcp -> 1/x), so this checks logic and rounding policy, not the
+// hardware approximations; the GPU parity tests do that.
+#include "../../godot_atmosphere_shader_b200/csrc/atmo_consts.h"
+#include "../../godot_atmosphere_shader_b200/csrc/atmo_device.cuh"
+
+using namespace b200atmo;
+
+extern "C" {
+
+typedef struct HostsimTextures {
+    const float* lut_pad;
+    const float* cube_pad;
+    int32_t cube_res;
+    const float* shape_pad;
+    int32_t nx, ny, nz;
+    const uint8_t* blue_noise;
+    int32_t bn_w, bn_h;
+} HostsimTextures;
+
+}  // extern "C"
+
+static DeviceTextures tex_of(const HostsimTextures* t) {
+    DeviceTextures d;
+    d.lut_pad = t->lut_pad;
+    d.cube_pad = t->cube_pad;
+    d.cube_res = t->cube_res;
+    d.shape_pad = t->shape_pad;
+    d.nx = t->nx; d.ny = t->ny; d.nz = t->nz;
+    d.blue_noise = t->blue_noise;
+    d.bn_w = t->bn_w; d.bn_h = t->bn_h;
+    return d;
+}
+
+template <int M, int L>
+static void run_rays(const DevConsts& c, const float* od, const float* dj, size_t n, float* rgba, uint8_t* disc) {
+    for (size_t i = 0; i < n; ++i) {
+        float4 out;
+        bool d = shade_ray<M, L>(c, mk3(od[4 * i], od[4 * i + 1], od[4 * i + 2]), mk3(dj[4 * i], dj[4 * i + 1], dj[4 * i + 2]),
+                                 od[4 * i + 3], dj[4 * i + 3], out);
+        rgba[4 * i] = out.x; rgba[4 * i + 1] = out.y; rgba[4 * i + 2] = out.z; rgba[4 * i + 3] = out.w;
+        if (disc) disc[i] = d ? 1 : 0;
+    }
+}
+
+extern "C" {
+
+void hostsim_render_rays(const B200AtmoParams* p, const int32_t variant[4], const B200AtmoFrame* fr, const HostsimTextures* t,
+                         const float* od, const float* dj, size_t n, float* rgba, uint8_t* disc) {
+    Variant v;
+    v.scatter_model = variant[0]; v.scatter_steps = variant[1]; v.cloud_steps = variant[2]; v.light_mode = variant[3];
+    DevConsts c;
+    consts_from_params(c, *p, v, tex_of(t));
+    consts_set_frame(c, *p, fr->planet_center_view, fr->sun_center_view, fr->inv_view);
+    const int key = v.scatter_model * 3 + v.light_mode;
+    switch (key) {
+        case 0: run_rays<0, 0>(c, od, dj, n, rgba, disc); break;
+        case 1: run_rays<0, 1>(c, od, dj, n, rgba, disc); break;
+        case 2: run_rays<0, 2>(c, od, dj, n, rgba, disc); break;
+        case 3: run_rays<1, 0>(c, od, dj, n, rgba, disc); break;
+        case 4: run_rays<1, 1>(c, od, dj, n, rgba, disc); break;
+        default: run_rays<1, 2>(c, od, dj, n, rgba, disc); break;
+    }
+}
+
+// frame front-end + frame constants (make_rays_kernel / b200atmo_make_rays on the host)
+void hostsim_make_rays(const B200AtmoParams* p, const B200AtmoCamera* cam, const HostsimTextures* t, const float* depth, int w,
+                       int h, float* od, float* dj, B200AtmoFrame* frame_out) {
+    Variant v;
+    DevConsts c;
+    consts_from_params(c, *p, v, tex_of(t));
+    consts_set_camera(c, *p, *cam, w, h, 0, h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            size_t i = size_t(y) * w + x;
+            f3 o, d;
+            float ld, jit;
+            make_ray(c, x, y, depth[i], o, d, ld, jit);
+            od[4 * i] = o.x; od[4 * i + 1] = o.y; od[4 * i + 2] = o.z; od[4 * i + 3] = ld;
+            dj[4 * i] = d.x; dj[4 * i + 1] = d.y; dj[4 * i + 2] = d.z; dj[4 * i + 3] = jit;
+        }
+    if (frame_out) {
+        for (int k = 0; k < 3; ++k) frame_out->planet_center_view[k] = c.C[k];
+        std::memcpy(frame_out->inv_view, c.inv_view_ray, sizeof(frame_out->inv_view));
+        // sun centre is not kept in DevConsts; recompute like consts_set_camera
+        float sc[4];
+        hostmath::mat4_mul_vec(cam->view, p->sun_position[0], p->sun_position[1], p->sun_position[2], 1.0f, sc);
+        for (int k = 0; k < 3; ++k) frame_out->sun_center_view[k] = sc[k];
+    }
+}
+
+float hostsim_sqrt_refined(float x) { float inv; return sqrt_refined(x, inv); }
+float hostsim_div_refined(float a, float b) { return div_refined(a, b, 1.0f / b); }
+int hostsim_floor_frac(float x, float* frac) { return floor_frac(x, *frac); }
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, libb200atmo.so) against the fp32 oracle.
+
+Tolerance: |got - want| <= 1e-4*|want| + 2e-6 per channel (helpers.RTOL/ATOL); integer / decision outputs
+(discard mask, LUT bits, cube layout, generated rays) must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+from godot_atmosphere_shader_b200 import abi, scenes
+from oracle import pyoracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {
+    # name: (scatter_model, scatter_steps, cloud_steps, light)   — the reference's shipped variant matrix
+    "no_clouds": (abi.SCATTER_V2, 8, 0, abi.LIGHT_NONE),
+    "clouds": (abi.SCATTER_V2, 8, 32, abi.LIGHT_CHEAP),
+    "clouds_high": (abi.SCATTER_V2, 8, 64, abi.LIGHT_CHEAP),
+    "clouds_high_rm": (abi.SCATTER_V2, 8, 64, abi.LIGHT_RAYMARCHED),
+    "v1_no_clouds": (abi.SCATTER_V1, 16, 0, abi.LIGHT_NONE),
+    "v1_clouds": (abi.SCATTER_V1, 16, 32, abi.LIGHT_CHEAP),
+    "v1_clouds_high": (abi.SCATTER_V1, 16, 64, abi.LIGHT_CHEAP),
+    # BASELINE.json scale-ups
+    "scatter32": (abi.SCATTER_V2, 32, 0, abi.LIGHT_NONE),
+    "scatter64": (abi.SCATTER_V2, 64, 0, abi.LIGHT_NONE),
+    "scatter32_clouds64": (abi.SCATTER_V2, 32, 64, abi.LIGHT_CHEAP),
+    "rm128": (abi.SCATTER_V2, 8, 128, abi.LIGHT_RAYMARCHED),
+    "odd_counts": (abi.SCATTER_V2, 5, 7, abi.LIGHT_RAYMARCHED),
+}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _setup(ctx, params, variant, textures=True):
+    shape, cube, bn = Hh.demo_textures()
+    ctx.set_params(params)
+    m, ns, nc, lm = variant
+    ctx.set_variant(ns, nc, lm, m)
+    ctx.upload_blue_noise(bn)
+    if textures:
+        ctx.upload_shape3d(shape)
+        ctx.upload_coverage_cube(cube)
+    return O.Textures(lut=O.bake_lut(params), shape=shape if textures else None, cube_faces=cube if textures else None,
+                      blue_noise=bn)
+
+
+def _render_rays_gpu(ctx, fr, od, dj):
+    torch = _torch()
+    n = od.shape[0]
+    d_od = torch.from_numpy(np.ascontiguousarray(od)).cuda()
+    d_dj = torch.from_numpy(np.ascontiguousarray(dj)).cuda()
+    d_rgba = torch.full((max(n, 1), 4), -7.0, dtype=torch.float32, device="cuda")
+    d_disc = torch.full((max(n, 1),), 9, dtype=torch.uint8, device="cuda")
+    ctx.render_rays(fr, d_od, d_dj, n, d_rgba, d_disc, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_rgba.cpu().numpy()[:n], d_disc.cpu().numpy()[:n]
+
+
+def test_lut_bake_bit_exact(cuda_ctx_factory):
+    ctx = cuda_ctx_factory()
+    for params in (scenes.demo_params(), scenes.template_params(), abi.default_params()):
+        ctx.set_params(params)
+        got = ctx.download_lut()
+        want = O.bake_lut(params)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        # the reference's RGBA8 viewport round trip (optical_depth.gdshader:33-43, baker.gd:75-77) is lossless
+        assert np.array_equal(got.view(np.uint32), O.bake_lut(params, via_rgba8=True).view(np.uint32))
+
+
+def test_lut_rebake_on_param_change(cuda_ctx_factory):
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    ctx.set_params(p)
+    a = ctx.download_lut()
+    n0 = ctx.launch_count
+    ctx.set_params(p)  # unchanged: no re-bake
+    ctx.download_lut()
+    assert ctx.launch_count == n0
+    p.density = 0.75  # _shader_params_affecting_optical_depth (planet_atmosphere.gd:79-81)
+    ctx.set_params(p)
+    b = ctx.download_lut()
+    assert ctx.launch_count == n0 + 1
+    assert not np.array_equal(a, b)
+    assert np.array_equal(b, O.bake_lut(p))
+
+
+@pytest.mark.parametrize("res", [1, 2, 5, 64])
+def test_cube_layout_bit_exact(cuda_ctx_factory, res):
+    ctx = cuda_ctx_factory()
+    rng = np.random.default_rng(res)
+    faces = rng.integers(0, 256, size=(6, res, res), dtype=np.uint8)
+    ctx.upload_coverage_cube(faces)
+    assert np.array_equal(ctx.download_cube_padded(), O.cube_build_padded(faces))
+
+
+@pytest.mark.parametrize("cam_name", ["A", "B", "A_orbit90_dp"])
+def test_make_rays_bit_exact(cuda_ctx_factory, cam_name):
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 160, 90
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["no_clouds"], textures=False)
+    cam = {"A": scenes.camera_a(w, h), "B": scenes.camera_b(w, h, p), "A_orbit90_dp": scenes.camera_a(w, h, 90.0)}[cam_name]
+    if cam_name.endswith("dp"):
+        cam.double_precision = 1
+    depth = scenes.synth_depth(cam, p, w, h)
+    od, dj, fr = O.make_rays(p, cam, tex, depth, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    d_od = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    d_dj = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    gfr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_od.cpu().numpy().view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(d_dj.cpu().numpy().view(np.uint32), dj.view(np.uint32))
+    assert bytes(gfr) == bytes(fr)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("cam_name", ["A", "B"])
+def test_frame_parity(cuda_ctx_factory, variant, cam_name):
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    heavy = VARIANTS[variant][3] == abi.LIGHT_RAYMARCHED
+    w, h = (96, 54) if heavy else (192, 108)
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS[variant])
+    cam = scenes.camera_a(w, h) if cam_name == "A" else scenes.camera_b(w, h, p)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    d_rgba = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+    d_disc = torch.full((h, w), 9, dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, d_rgba, d_disc, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    m, ns, nc, lm = VARIANTS[variant]
+    ref, rdisc = O.render_frame(p, O.variant(ns, nc, lm, m), cam, tex, depth, w, h, threads=0)
+    assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+    Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"{variant}/{cam_name}")
+
+
+@pytest.mark.parametrize("variant", ["no_clouds", "clouds_high", "clouds_high_rm", "v1_clouds"])
+def test_random_rays_parity(cuda_ctx_factory, variant):
+    """Ray-batch API with general origins (inside / outside / grazing / missing), ragged size."""
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    p.sphere_depth_factor = 0.25
+    rot = 0.37
+    p.cloud_coverage_rotation[:] = (np.cos(rot), np.sin(rot), -np.sin(rot), np.cos(rot))  # Transform2D().rotated(a)
+    tex = _setup(ctx, p, VARIANTS[variant])
+    n = 3001 if VARIANTS[variant][3] == abi.LIGHT_RAYMARCHED else 20011
+    od, dj, fr = Hh.random_rays(n, p, seed=11)
+    got, gdisc = _render_rays_gpu(ctx, fr, od, dj)
+    m, ns, nc, lm = VARIANTS[variant]
+    ref, rdisc = O.render_rays(p, O.variant(ns, nc, lm, m), fr, tex, od, dj, threads=0)
+    assert 0.02 < rdisc.mean() < 0.98  # the set really mixes hits and misses
+    assert np.array_equal(gdisc, rdisc)
+    assert np.all(got[rdisc == 1] == 0.0)
+    Hh.assert_rgba_close(got, ref, what=variant)
+
+
+def test_template_scene_parity(cuda_ctx_factory):
+    """planet_atmosphere.tscn parameter set (R=1, H=0.2, u_density=10) — BASELINE config[0] size 256x256, N=8."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w = h = 256
+    p = scenes.template_params()
+    tex = _setup(ctx, p, VARIANTS["no_clouds"], textures=False)
+    cam = scenes.make_camera((0.2, 0.1, 2.6), (0.0, 0.0, -1.0), aspect=1.0, near=0.05, far=100.0)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    d_disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, torch.from_numpy(depth).cuda(), w, h, d_rgba, d_disc)
+    torch.cuda.synchronize()
+    ref, rdisc = O.render_frame(p, O.variant(8), cam, tex, depth, w, h, threads=0)
+    assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+    Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what="template")
+
+
+def test_unset_textures_mean_uniform_cover(cuda_ctx_factory):
+    """No cube / shape uploaded: samplers read white ("cover the whole atmosphere uniformly", README.md:46)."""
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds"], textures=False)
+    od, dj, fr = Hh.random_rays(5000, p, seed=5)
+    got, gdisc = _render_rays_gpu(ctx, fr, od, dj)
+    ref, rdisc = O.render_rays(p, O.variant(8, 32, abi.LIGHT_CHEAP), fr, tex, od, dj, threads=0)
+    assert np.array_equal(gdisc, rdisc)
+    Hh.assert_rgba_close(got, ref, what="unset textures")
+
+
+def test_edge_sizes(cuda_ctx_factory):
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds"])
+    for n in (0, 1, 127, 128, 129):
+        od, dj, fr = Hh.random_rays(max(n, 1), p, seed=n)
+        od, dj = od[:n], dj[:n]
+        got, gdisc = _render_rays_gpu(ctx, fr, od, dj)
+        if n == 0:
+            continue
+        ref, rdisc = O.render_rays(p, O.variant(8, 32, abi.LIGHT_CHEAP), fr, tex, od, dj)
+        assert np.array_equal(gdisc, rdisc)
+        Hh.assert_rgba_close(got, ref, what=f"n={n}")
+
+
+def test_frame_api_equals_ray_api_and_host_api(cuda_ctx_factory):
+    """render_frame == make_rays + render_rays == render_frame_host == render_rays_host, bit for bit."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 200, 120
+    p = scenes.demo_params()
+    _setup(ctx, p, VARIANTS["clouds"])
+    cam = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    a = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    ad = torch.empty((h * w,), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, a, ad)
+    d_od = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    d_dj = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj)
+    b = torch.empty_like(a)
+    bd = torch.empty_like(ad)
+    ctx.render_rays(fr, d_od, d_dj, h * w, b, bd)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(ad, bd)
+    hc = np.empty((h * w, 4), np.float32)
+    hd = np.empty((h * w,), np.uint8)
+    ctx.render_frame_host(cam, depth, w, h, hc, hd)
+    assert np.array_equal(hc, a.cpu().numpy()) and np.array_equal(hd, ad.cpu().numpy())
+    he = np.empty((h * w, 4), np.float32)
+    hf = np.empty((h * w,), np.uint8)
+    ctx.render_rays_host(fr, d_od.cpu().numpy(), d_dj.cpu().numpy(), h * w, he, hf)
+    assert np.array_equal(he, hc) and np.array_equal(hf, hd)
+
+
+def test_full_size_properties(cuda_ctx_factory):
+    """BASELINE config[1] size (1920x1080, N=32): size-independent properties instead of a full oracle run."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 1920, 1080
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["scatter32"])
+    cam = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    full = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    fdisc = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, full, fdisc)
+    # (1) determinism
+    again = torch.zeros_like(full)
+    ctx.render_frame(cam, d_depth, w, h, again, None)
+    # (2) row-shard invariance: 8 bands (the multi-GPU partition) reassemble to the same bits
+    banded = torch.zeros_like(full)
+    for k in range(8):
+        ctx.render_frame(cam, d_depth, w, h, banded, None, row_begin=h * k // 8, row_end=h * (k + 1) // 8)
+    torch.cuda.synchronize()
+    assert torch.equal(full, again)
+    assert torch.equal(full, banded)
+    f = full.cpu().numpy()
+    d = fdisc.cpu().numpy()
+    # (3) ranges: rgb in [0, modulate], alpha in [0, 0.99]; discarded pixels are exactly zero
+    assert np.isfinite(f).all()
+    assert f[..., 3].min() >= 0.0 and f[..., 3].max() <= 0.99 + 1e-7
+    for c in range(3):
+        assert f[..., c].min() >= 0.0 and f[..., c].max() <= p.atmosphere_modulate[c] + 1e-6
+    assert np.all(f[d == 1] == 0.0) and 0.0 < d.mean() < 0.5
+    # (4) a strided 1/97 sample of the pixels against the oracle (covers the whole frame)
+    od, dj, fr = O.make_rays(p, cam, tex, depth, w, h)
+    sel = np.arange(0, w * h, 97)
+    ref, rdisc = O.render_rays(p, O.variant(32), fr, tex, od[sel], dj[sel], threads=0)
+    assert np.array_equal(d.reshape(-1)[sel], rdisc)
+    Hh.assert_rgba_close(f.reshape(-1, 4)[sel], ref, what="1080p sample")
+
+
+def test_errors(cuda_ctx_factory):
+    from godot_atmosphere_shader_b200.context import B200AtmoError
+    ctx = cuda_ctx_factory()
+    with pytest.raises(B200AtmoError):
+        ctx.set_variant(0)
+    with pytest.raises(B200AtmoError):
+        ctx.set_variant(8, 0, abi.LIGHT_CHEAP)
+    with pytest.raises(B200AtmoError):
+        ctx.set_variant(8, 0, 7)
+    with pytest.raises(B200AtmoError):
+        ctx.upload_blue_noise(np.zeros((100, 100), np.uint8))
+    fr = abi.B200AtmoFrame()
+    with pytest.raises(B200AtmoError):
+        ctx.render_rays(fr, None, None, 10, None)

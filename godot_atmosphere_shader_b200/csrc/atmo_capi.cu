@@ -20,6 +20,7 @@ struct b200atmo_ctx {
     bool lut_stale = true;
     float* d_lut = nullptr;       // [256][256]
     float* d_lut_pad = nullptr;   // [258][258]
+    float4* d_lut_cells = nullptr; // [257][257] bilinear cells
     uint8_t* d_cube_raw = nullptr;
     uint8_t* d_cube_pad_u8 = nullptr;
     float* d_cube_pad = nullptr;
@@ -85,6 +86,7 @@ int ensure(b200atmo_ctx* ctx, void** p, size_t* cap, size_t need) {
 DeviceTextures textures_of(const b200atmo_ctx* ctx) {
     DeviceTextures t;
     t.lut_pad = ctx->d_lut_pad;
+    t.lut_cells = ctx->d_lut_cells;
     t.cube_pad = ctx->d_cube_pad;
     t.cube_res = ctx->cube_res;
     t.shape_pad = ctx->d_shape_pad;
@@ -100,8 +102,8 @@ DeviceTextures textures_of(const b200atmo_ctx* ctx) {
 int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
     if (!ctx->lut_stale) return B200ATMO_OK;
     CU_TRY(ctx, launch_bake_lut(ctx->params.planet_radius, ctx->params.atmosphere_height, ctx->params.density, ctx->d_lut,
-                                ctx->d_lut_pad, s));
-    ctx->launches++;
+                                ctx->d_lut_pad, ctx->d_lut_cells, s));
+    ctx->launches += 2;
     // re-bakes are rare (R, H or u_density changed); finishing here keeps later launches on OTHER streams safe
     CU_TRY(ctx, cudaStreamSynchronize(s));
     ctx->lut_stale = false;
@@ -216,6 +218,7 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
     } while (0)
     CREATE_TRY(cudaMalloc(&ctx->d_lut, sizeof(float) * kLut * kLut));
     CREATE_TRY(cudaMalloc(&ctx->d_lut_pad, sizeof(float) * kLutPad * kLutPad));
+    CREATE_TRY(cudaMalloc(&ctx->d_lut_cells, sizeof(float4) * kLutCells * kLutCells));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[0], cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[1], cudaStreamNonBlocking));
 #undef CREATE_TRY
@@ -233,6 +236,7 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
+    cudaFree(ctx->d_lut_cells);
     cudaFree(ctx->d_cube_raw);
     cudaFree(ctx->d_cube_pad_u8);
     cudaFree(ctx->d_cube_pad);

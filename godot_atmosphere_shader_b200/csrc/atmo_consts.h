@@ -19,6 +19,7 @@ struct Variant {
 
 struct DeviceTextures {
     const float* lut_pad = nullptr;
+    const float4* lut_cells = nullptr;
     const float* cube_pad = nullptr;
     int cube_res = 0;
     const float* shape_pad = nullptr;
@@ -63,6 +64,7 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
     c.rho2 = c.rho * c.rho;
     c.day_night_scale = p.day_night_transition_scale;
     c.lut_pad = t.lut_pad;
+    c.lut_cells = t.lut_cells;
     // clouds
     c.cloud_bottom_h = p.planet_radius + p.cloud_bottom * p.atmosphere_height;  // cloud_funcs:260
     c.cloud_top_h = p.planet_radius + p.cloud_top * p.atmosphere_height;        // cloud_funcs:261

@@ -27,6 +27,7 @@
 #ifdef __CUDACC__
 #define B200_DEV __device__ __forceinline__
 #define B200_UNROLL(n) B200_PRAGMA(unroll n)
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #else
 #define B200_UNROLL(n)
 // ---- host simulation shims (tests/hostsim only) ----
@@ -38,6 +39,7 @@ struct float4 {
 };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float __ldg(const float* p) { return *p; }
+static inline float4 ldg4(const float4* p) { return *p; }
 static inline float __saturatef(float x) { return x != x ? 0.0f : (x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x)); }
 static inline int __float_as_int(float f) {
     int i;
@@ -46,6 +48,7 @@ static inline int __float_as_int(float f) {
 }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 #endif
 
 namespace b200atmo {
@@ -202,6 +205,34 @@ B200_DEV float sample_shape(const float* __restrict__ shp, int nx, int ny, int n
     return lerp_fma(lerp_fma(c00, c10, fy), lerp_fma(c01, c11, fy), fz);
 }
 
+// Bilinear LUT fetch for the scatter loop from the CELL layout (atmo_kernels.cu: lut_cells_kernel):
+//   cell(xi, yi) = float4(t00, t10 - t00, t01 - t00, (t11 - t01) - (t10 - t00))   for padded texels (xi..xi+1, yi..yi+1)
+// so texture(LUT, uv) = t00 + dx*fx + fy*(dy + dxy*fx): ONE 16-byte load and three FMAs.
+// Inputs: mu = dot(up, sun_dir) in [-1,1]; y = 1 - height_ratio in [0,1].
+// Padded texel coordinates: xp = u*256 - 0.5 + 1 = 128*mu + 128.5, yp = 256*(1-y) + 0.5. floor(xp) = rn(xp - 0.5) comes
+// out of ONE fma against the 1.5*2^23 constant (integer in the low mantissa bits), the fraction out of a second fma
+// with the integer part folded into the addend. The LUT is smooth, so (unlike the noise textures) its coordinates
+// need not reproduce the shader's rounding; the fused forms are at least as accurate.
+B200_DEV float4 make_lut_cell(const float* __restrict__ lut_pad, int xi, int yi) {
+    const float* p = lut_pad + yi * kLutPad + xi;
+    const float t00 = p[0], t10 = p[1], t01 = p[kLutPad], t11 = p[kLutPad + 1];
+    const float dx = t10 - t00, dx1 = t11 - t01;
+    return make_float4(t00, dx, t01 - t00, dx1 - dx);
+}
+B200_DEV float sample_lut_cells(const float4* __restrict__ cells, float mu, float y) {
+    const float xm = fmaf(mu, 128.0f, kMagic + 128.0f);
+    const float ym = fmaf(y, -256.0f, kMagic + 256.0f);
+    const float fx = fmaf(mu, 128.0f, 128.5f - (xm - kMagic));
+    const float fy = fmaf(y, -256.0f, 256.5f - (ym - kMagic));
+    // row*257 + col with both magic biases folded into one constant (mod 2^32); the unsigned min turns the
+    // garbage of a NaN coordinate (pos == planet centre) into an in-range read instead of a fault
+    unsigned off = unsigned(__float_as_int(ym)) * unsigned(kLutCells) + unsigned(__float_as_int(xm)) -
+                   unsigned(kMagicBits) * unsigned(kLutCells + 1);
+    off = min(off, unsigned(kLutCells * kLutCells - 1));
+    const float4 q = ldg4(cells + off);
+    return fmaf(fmaf(q.w, fx, q.z), fy, fmaf(q.y, fx, q.x));
+}
+
 // ------------------------------------------------------------------------------------------------
 // include/atmosphere_funcs_v2.gdshaderinc:32-101 — N-step in-scatter march against the baked LUT
 // ------------------------------------------------------------------------------------------------
@@ -213,20 +244,20 @@ B200_DEV float4 scatter_v2(const DevConsts& c, f3 o, f3 d, float t_begin, float 
     const f3 dstep = d * step_len;
     const float ld_scale = c.rho2 * step_len;  // get_atmosphere_density()*u_density*step_len = y^3 * rho^2 * step_len
     const float k0 = c.neg_coef_log2e[0], k1 = c.neg_coef_log2e[1], k2 = c.neg_coef_log2e[2];
+    const float neg_inv_H = -c.inv_H;
     float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, view_od = 0.0f;
 
 B200_UNROLL(2)
     for (int i = 0; i < steps; ++i) {
-        const f3 rel = pos - C;
-        const float d2 = dot3(rel, rel);
+        const f3 rel = pos - C;                                             // exact: carries the shader's position rounding
+        const float d2 = fmaf(rel.z, rel.z, fmaf(rel.y, rel.y, rel.x * rel.x));
+        const float sd = fmaf(rel.z, sun.z, fmaf(rel.y, sun.y, rel.x * sun.x));
         float inv;
         const float dist = sqrt_refined(d2, inv);                           // distance(pos, planet_center)
-        const float hr = __saturatef(div_refined(dist - c.R, c.H, c.inv_H)); // height_ratio :17-18 == density's h
-        float mu = fmaf(rel.z, sun.z, fmaf(rel.y, sun.y, rel.x * sun.x)) * inv;  // dot(normalize(pos-C), sun_dir) :19-20
-        mu = fminf(fmaxf(mu, -1.0f), 1.0f);
-        const float sun_od = sample_lut(c.lut_pad, fmaf(0.5f, mu, 0.5f), hr);  // :20,28
-        const float y = 1.0f - hr;                                          // atmosphere_common:14-17
-        const float ld_step = y * y * y * ld_scale;                         // local_density * step_len, :64-65
+        // y = 1 - clamp((dist-R)/H, 0, 1) in one rounding (atmosphere_common:13-15); height_ratio (:17-18) = 1 - y
+        const float y = __saturatef(fmaf(dist - c.R, neg_inv_H, 1.0f));
+        const float sun_od = sample_lut_cells(c.lut_cells, sd * inv, y);    // dot(normalize(pos-C), sun_dir) :19-20, fetch :28
+        const float ld_step = (y * y) * (y * ld_scale);                     // local_density * step_len, :64-65
         view_od += ld_step;                                                 // :66
         const float od = sun_od + view_od;
         const float T0 = ex2_approx(od * k0), T1 = ex2_approx(od * k1), T2 = ex2_approx(od * k2);  // :71-73

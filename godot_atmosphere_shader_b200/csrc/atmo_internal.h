@@ -2,6 +2,9 @@
 // Not installed; the public surface is include/b200atmo.h.
 #pragma once
 
+#ifndef __CUDACC__
+struct float4;
+#endif
 #include <stddef.h>
 #include <stdint.h>
 
@@ -11,6 +14,7 @@ namespace b200atmo {
 
 constexpr int kLut = B200ATMO_LUT_SIZE;      // 256
 constexpr int kLutPad = kLut + 2;            // clamp-to-edge apron of one texel on every side
+constexpr int kLutCells = kLut + 1;          // bilinear cells between padded texels: 257 x 257
 
 // Everything a render kernel needs, passed by value as a __grid_constant__ kernel parameter.
 // Host code (atmo_consts.h) fills it with plain fp32 arithmetic in the shader's op order, no FMA
@@ -28,6 +32,7 @@ struct DevConsts {
     float inv_H;           // 1/H, correctly rounded
     float rho2;            // rho*rho (density is applied twice, funcs_v2:65)
     const float* lut_pad;  // [kLutPad][kLutPad] fp32
+    const float4* lut_cells;  // [kLutCells][kLutCells] bilinear coefficient cells (t00, dx, dy, dxy)
     // --- scattering v1 ---
     float day0[3], day1[3], night0[3], night1[3];
     float day_night_scale;
@@ -70,7 +75,7 @@ struct RayIO {
 
 #ifdef __CUDACC__
 // kernels (atmo_kernels.cu)
-cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, cudaStream_t s);
+cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, float4* d_lut_cells, cudaStream_t s);
 cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, cudaStream_t s);
 cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, cudaStream_t s);
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);

@@ -44,8 +44,18 @@ __global__ void __launch_bounds__(256) bake_lut_kernel(float R, float H, float r
         for (int x2 = xs; x2 <= xe; ++x2) lut_pad[y2 * kLutPad + x2] = od;
 }
 
-cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, cudaStream_t s) {
+// Bilinear coefficient cells for the scatter loop: one float4 per pair of adjacent padded texel rows/columns,
+// (t00, dx, dy, dxy) with t(x,y) ~ t00 + dx*fx + fy*(dy + dxy*fx). 257*257*16 B = 1.06 MB, L2-resident.
+__global__ void __launch_bounds__(256) lut_cells_kernel(const float* __restrict__ lut_pad, float4* __restrict__ cells) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= kLutCells * kLutCells) return;
+    const int yi = idx / kLutCells, xi = idx % kLutCells;
+    cells[idx] = make_lut_cell(lut_pad, xi, yi);
+}
+
+cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, float4* d_lut_cells, cudaStream_t s) {
     bake_lut_kernel<<<dim3(kLut / 16, kLut / 16), 256, 0, s>>>(R, H, rho, d_lut, d_lut_pad);
+    lut_cells_kernel<<<(kLutCells * kLutCells + 255) / 256, 256, 0, s>>>(d_lut_pad, d_lut_cells);
     return cudaGetLastError();
 }
 

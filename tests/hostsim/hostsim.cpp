@@ -22,9 +22,15 @@ typedef struct HostsimTextures {
 
 }  // extern "C"
 
+#include <vector>
+static std::vector<float4> g_cells;  // host restatement of lut_cells_kernel (single-threaded test helper)
 static DeviceTextures tex_of(const HostsimTextures* t) {
     DeviceTextures d;
     d.lut_pad = t->lut_pad;
+    g_cells.resize(size_t(kLutCells) * kLutCells);
+    for (int yi = 0; yi < kLutCells; ++yi)
+        for (int xi = 0; xi < kLutCells; ++xi) g_cells[size_t(yi) * kLutCells + xi] = make_lut_cell(t->lut_pad, xi, yi);
+    d.lut_cells = g_cells.data();
     d.cube_pad = t->cube_pad;
     d.cube_res = t->cube_res;
     d.shape_pad = t->shape_pad;

@@ -35,6 +35,16 @@ def _torch():
     return torch
 
 
+def _params_for(variant, base=None):
+    """Scene "demo"; the v1 "lite" model gets a v1-sized density: its `factor *= 1 - density*step_len`
+    (funcs_v1:39) is numerically chaotic once density*step_len > 1 (the fp32 and fp64 oracles then disagree on
+    a third of the rays), and the demo scene's u_density = 0.5 with 16 steps over ~80 units is far in that regime."""
+    p = base if base is not None else scenes.demo_params()
+    if variant[0] == abi.SCATTER_V1:
+        p.density = 0.02
+    return p
+
+
 def _setup(ctx, params, variant, textures=True):
     shape, cube, bn = Hh.demo_textures()
     ctx.set_params(params)
@@ -126,7 +136,7 @@ def test_frame_parity(cuda_ctx_factory, variant, cam_name):
     ctx = cuda_ctx_factory()
     heavy = VARIANTS[variant][3] == abi.LIGHT_RAYMARCHED
     w, h = (96, 54) if heavy else (192, 108)
-    p = scenes.demo_params()
+    p = _params_for(VARIANTS[variant])
     tex = _setup(ctx, p, VARIANTS[variant])
     cam = scenes.camera_a(w, h) if cam_name == "A" else scenes.camera_b(w, h, p)
     depth = scenes.synth_depth(cam, p, w, h)
@@ -145,7 +155,7 @@ def test_frame_parity(cuda_ctx_factory, variant, cam_name):
 def test_random_rays_parity(cuda_ctx_factory, variant):
     """Ray-batch API with general origins (inside / outside / grazing / missing), ragged size."""
     ctx = cuda_ctx_factory()
-    p = scenes.demo_params()
+    p = _params_for(VARIANTS[variant])
     p.sphere_depth_factor = 0.25
     rot = 0.37
     p.cloud_coverage_rotation[:] = (np.cos(rot), np.sin(rot), -np.sin(rot), np.cos(rot))  # Transform2D().rotated(a)

@@ -1,0 +1,96 @@
+"""CPU-only checks of the PRODUCT's device code compiled for the host (tests/hostsim): logic, exact-arithmetic
+policy and texture layouts, without a GPU. The MUFU approximations are replaced by libm here; the GPU parity
+tests (-m gpu) cover the real hardware path."""
+import numpy as np
+import pytest
+
+from godot_atmosphere_shader_b200 import abi, scenes
+from oracle import pyoracle as O
+from tests import helpers as Hh
+
+
+@pytest.fixture(scope="module")
+def scene():
+    p = scenes.demo_params()
+    shape, cube, bn = Hh.demo_textures()
+    lut = O.bake_lut(p)
+    return p, Hh.HostsimScene(lut, shape, cube, bn), O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+
+
+@pytest.mark.parametrize("cam_name", ["A", "B", "A_dp"])
+def test_ray_generation_bit_exact(scene, cam_name):
+    p, hs, otex = scene
+    w, h = 96, 54
+    cam = scenes.camera_b(w, h, p) if cam_name == "B" else scenes.camera_a(w, h, 30.0)
+    if cam_name == "A_dp":
+        cam.double_precision = 1
+    depth = scenes.synth_depth(cam, p, w, h)
+    od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
+    od2, dj2, fr2 = hs.make_rays(p, cam, depth, w, h)
+    assert np.array_equal(od.view(np.uint32), od2.view(np.uint32))
+    assert np.array_equal(dj.view(np.uint32), dj2.view(np.uint32))
+    assert bytes(fr) == bytes(fr2)
+
+
+VARIANTS = [(0, 8, 0, 0), (0, 32, 0, 0), (0, 8, 32, 1), (0, 8, 64, 2), (1, 16, 0, 0), (1, 16, 32, 1), (0, 3, 5, 2)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("cam_name", ["A", "B"])
+def test_device_logic_matches_oracle(scene, variant, cam_name):
+    p, hs, otex = scene
+    p = p.copy()
+    if variant[0] == abi.SCATTER_V1:
+        p.density = 0.02  # see tests/test_gpu_parity.py::_params_for
+        lut = O.bake_lut(p)
+        shape, cube, bn = Hh.demo_textures()
+        hs = Hh.HostsimScene(lut, shape, cube, bn)
+        otex = O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+    w, h = (64, 36) if variant[3] == 2 else (128, 72)
+    cam = scenes.camera_a(w, h) if cam_name == "A" else scenes.camera_b(w, h, p)
+    depth = scenes.synth_depth(cam, p, w, h)
+    od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
+    m, ns, nc, lm = variant
+    var = O.variant(ns, nc, lm, m)
+    ref, rdisc = O.render_rays(p, var, fr, otex, od, dj)
+    got, gdisc = hs.render_rays(p, var, fr, od, dj)
+    assert np.array_equal(gdisc, rdisc)
+    Hh.assert_rgba_close(got, ref, what=str(variant))
+
+
+def test_random_rays_and_rotation(scene):
+    p, hs, otex = scene
+    p = p.copy()
+    p.sphere_depth_factor = 0.25
+    p.cloud_coverage_rotation[:] = (np.cos(0.37), np.sin(0.37), -np.sin(0.37), np.cos(0.37))
+    od, dj, fr = Hh.random_rays(6000, p, seed=11)
+    ref, rdisc = O.render_rays(p, O.variant(8, 32, 1), fr, otex, od, dj)
+    got, gdisc = hs.render_rays(p, O.variant(8, 32, 1), fr, od, dj)
+    assert np.array_equal(gdisc, rdisc)
+    assert 0.02 < rdisc.mean() < 0.98
+    Hh.assert_rgba_close(got, ref)
+
+
+def test_refined_sqrt_and_div_are_ieee():
+    """sqrt_refined / div_refined (csrc/atmo_device.cuh) equal the IEEE result (host build: exact reciprocal seeds)."""
+    L = Hh.hostsim()
+    rng = np.random.default_rng(0)
+    xs = np.float32(rng.uniform(1e-3, 3e4, size=20000))
+    for x in xs[:5000]:
+        assert L.hostsim_sqrt_refined(float(x)) == float(np.sqrt(np.float32(x)))
+    a = np.float32(rng.uniform(-8, 8, size=5000))
+    b = np.float32(rng.uniform(0.5, 12, size=5000))
+    for x, y in zip(a, b):
+        assert L.hostsim_div_refined(float(x), float(y)) == float(np.float32(x) / np.float32(y))
+
+
+def test_magic_floor():
+    import ctypes as C
+    L = Hh.hostsim()
+    fr = C.c_float()
+    for x in (0.0, 0.25, 0.999, 1.0, 1.5, 255.75, 256.49, -0.25, -0.5, 4096.5, 100000.125):
+        i = L.hostsim_floor_frac(C.c_float(x), C.byref(fr))
+        # same point of a continuous interpolant: i + frac == x, frac in [0, 1]
+        x = float(np.float32(x))
+        assert i + fr.value == pytest.approx(x, abs=1e-6) and -1e-6 <= fr.value <= 1.0 + 1e-6
+        assert i in (int(np.floor(x)), int(np.floor(x)) - 1)

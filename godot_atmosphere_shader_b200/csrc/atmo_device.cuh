@@ -216,47 +216,77 @@ B200_DEV float sample_shape(const float* __restrict__ shp, int nx, int ny, int n
 B200_DEV float4 make_lut_cell(const float* __restrict__ lut_pad, int xi, int yi) {
     const float* p = lut_pad + yi * kLutPad + xi;
     const float t00 = p[0], t10 = p[1], t01 = p[kLutPad], t11 = p[kLutPad + 1];
-    const float dx = t10 - t00, dx1 = t11 - t01;
-    return make_float4(t00, dx, t01 - t00, dx1 - dx);
+    const float dx = t10 - t00, dy = t01 - t00, dxy = (t11 - t01) - dx;
+    // expansion about the cell centre, g,h in [-0.5, 0.5]: t = tc + dxc*g + h*(dyc + dxy*g)
+    return make_float4(t00 + 0.5f * dx + 0.5f * dy + 0.25f * dxy, dx + 0.5f * dxy, dy + 0.5f * dxy, dxy);
 }
-B200_DEV float sample_lut_cells(const float4* __restrict__ cells, float mu, float y) {
-    const float xm = fmaf(mu, 128.0f, kMagic + 128.0f);
-    const float ym = fmaf(y, -256.0f, kMagic + 256.0f);
-    const float fx = fmaf(mu, 128.0f, 128.5f - (xm - kMagic));
-    const float fy = fmaf(y, -256.0f, 256.5f - (ym - kMagic));
-    // row*257 + col with both magic biases folded into one constant (mod 2^32); the unsigned min turns the
-    // garbage of a NaN coordinate (pos == planet centre) into an in-range read instead of a fault
-    unsigned off = unsigned(__float_as_int(ym)) * unsigned(kLutCells) + unsigned(__float_as_int(xm)) -
-                   unsigned(kMagicBits) * unsigned(kLutCells + 1);
-    off = min(off, unsigned(kLutCells * kLutCells - 1));
-    const float4 q = ldg4(cells + off);
-    return fmaf(fmaf(q.w, fx, q.z), fy, fmaf(q.y, fx, q.x));
+
+// Register-resident loop constants: an opaque move stops ptxas from re-materialising them (MOV / LDC)
+// inside the march loop, which is issue-bound.
+#ifdef __CUDACC__
+B200_DEV float pin_reg(float v) {
+    asm volatile("mov.f32 %0, %0;" : "+f"(v));
+    return v;
 }
+B200_DEV unsigned pin_reg(unsigned v) {
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
+}
+B200_DEV const float4* pin_reg(const float4* v) {
+    asm volatile("mov.b64 %0, %0;" : "+l"(v));
+    return v;
+}
+#else
+B200_DEV float pin_reg(float v) { return v; }
+B200_DEV unsigned pin_reg(unsigned v) { return v; }
+B200_DEV const float4* pin_reg(const float4* v) { return v; }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // include/atmosphere_funcs_v2.gdshaderinc:32-101 — N-step in-scatter march against the baked LUT
+//
+// LUT fetch (funcs_v2:14-29) from the CELL layout (atmo_kernels.cu: lut_cells_kernel): one float4 per pair of adjacent
+// padded texel rows/columns holding the bilinear patch expanded about the cell centre, so texture(LUT, uv) is ONE 16-byte
+// load and three FMAs. Padded texel coordinates: xp = u*256 + 0.5 = 128*mu + 128.5, yp = 256*(1-y) + 0.5 with
+// mu = dot(up, sun_dir), y = 1 - height_ratio. The cell index n = floor(xp) = rn(xp - 0.5) comes out of ONE add against
+// the 1.5*2^23 constant (integer in the low mantissa bits) and the centred fraction g = (xp - 0.5) - n out of two more.
+// The LUT is smooth, so (unlike the noise textures) its coordinates need not reproduce the shader's rounding.
 // ------------------------------------------------------------------------------------------------
 B200_DEV float4 scatter_v2(const DevConsts& c, f3 o, f3 d, float t_begin, float t_end, float jitter) {
     const int steps = c.scatter_steps;
-    const f3 C = ld3(c.C), sun = ld3(c.sun_dir);
+    const f3 C = ld3(c.C);
+    const f3 sun128 = mk3(c.sun_dir[0] * 128.0f, c.sun_dir[1] * 128.0f, c.sun_dir[2] * 128.0f);  // exact scaling
     const float step_len = (t_end - t_begin) / float(steps);
     f3 pos = o + d * t_begin;   // pos0, :57-58 (exact)
     const f3 dstep = d * step_len;
     const float ld_scale = c.rho2 * step_len;  // get_atmosphere_density()*u_density*step_len = y^3 * rho^2 * step_len
     const float k0 = c.neg_coef_log2e[0], k1 = c.neg_coef_log2e[1], k2 = c.neg_coef_log2e[2];
-    const float neg_inv_H = -c.inv_H;
+    const float neg_inv_H = pin_reg(-c.inv_H);
+    const float n256 = pin_reg(-256.0f);
+    constexpr unsigned off_bias = 0u - unsigned(kMagicBits) * unsigned(kLutCells + 1);  // both magic biases, mod 2^32
+    const float4* cells = pin_reg(c.lut_cells);
     float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, view_od = 0.0f;
 
-B200_UNROLL(2)
+B200_UNROLL(4)
     for (int i = 0; i < steps; ++i) {
         const f3 rel = pos - C;                                             // exact: carries the shader's position rounding
         const float d2 = fmaf(rel.z, rel.z, fmaf(rel.y, rel.y, rel.x * rel.x));
-        const float sd = fmaf(rel.z, sun.z, fmaf(rel.y, sun.y, rel.x * sun.x));
+        const float sd = fmaf(rel.z, sun128.z, fmaf(rel.y, sun128.y, rel.x * sun128.x));
         float inv;
         const float dist = sqrt_refined(d2, inv);                           // distance(pos, planet_center)
         // y = 1 - clamp((dist-R)/H, 0, 1) in one rounding (atmosphere_common:13-15); height_ratio (:17-18) = 1 - y
         const float y = __saturatef(fmaf(dist - c.R, neg_inv_H, 1.0f));
-        const float sun_od = sample_lut_cells(c.lut_cells, sd * inv, y);    // dot(normalize(pos-C), sun_dir) :19-20, fetch :28
+        const float mu128 = sd * inv;                                       // 128 * dot(normalize(pos-C), sun_dir), :19-20
+        const float xm = mu128 + (kMagic + 128.0f);                         // integer part n_x in the low mantissa bits
+        const float ym = fmaf(y, n256, kMagic + 256.0f);
+        const float g = mu128 - (xm - (kMagic + 128.0f));                   // centred fractions in [-0.5, 0.5]
+        const float h = fmaf(y, n256, 256.0f - (ym - kMagic));
+        // row*257 + col; the unsigned min turns the garbage of a NaN coordinate (pos == planet centre) into an
+        // in-range read instead of a fault
+        unsigned off = unsigned(__float_as_int(ym)) * unsigned(kLutCells) + unsigned(__float_as_int(xm));
+        off = min(off + off_bias, unsigned(kLutCells * kLutCells - 1));
+        const float4 q = ldg4(cells + off);                                 // :28
+        const float sun_od = fmaf(fmaf(q.w, g, q.z), h, fmaf(q.y, g, q.x));
         const float ld_step = (y * y) * (y * ld_scale);                     // local_density * step_len, :64-65
         view_od += ld_step;                                                 // :66
         const float od = sun_od + view_od;

@@ -32,7 +32,7 @@ struct DevConsts {
     float inv_H;           // 1/H, correctly rounded
     float rho2;            // rho*rho (density is applied twice, funcs_v2:65)
     const float* lut_pad;  // [kLutPad][kLutPad] fp32
-    const float4* lut_cells;  // [kLutCells][kLutCells] bilinear coefficient cells (t00, dx, dy, dxy)
+    const float4* lut_cells;  // [kLutCells][kLutCells] bilinear patches expanded about the cell centre (tc, dxc, dyc, dxy)
     // --- scattering v1 ---
     float day0[3], day1[3], night0[3], night1[3];
     float day_night_scale;

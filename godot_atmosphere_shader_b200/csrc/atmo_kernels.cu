@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) bake_lut_kernel(float R, float H, float r
         for (int x2 = xs; x2 <= xe; ++x2) lut_pad[y2 * kLutPad + x2] = od;
 }
 
-// Bilinear coefficient cells for the scatter loop: one float4 per pair of adjacent padded texel rows/columns,
-// (t00, dx, dy, dxy) with t(x,y) ~ t00 + dx*fx + fy*(dy + dxy*fx). 257*257*16 B = 1.06 MB, L2-resident.
+// Bilinear cells for the scatter loop: one float4 per pair of adjacent padded texel rows/columns holding the
+// patch expanded about the cell centre (make_lut_cell). 257*257*16 B = 1.06 MB, L2-resident.
 __global__ void __launch_bounds__(256) lut_cells_kernel(const float* __restrict__ lut_pad, float4* __restrict__ cells) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= kLutCells * kLutCells) return;

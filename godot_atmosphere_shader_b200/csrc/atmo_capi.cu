@@ -24,9 +24,11 @@ struct b200atmo_ctx {
     uint8_t* d_cube_raw = nullptr;
     uint8_t* d_cube_pad_u8 = nullptr;
     float* d_cube_pad = nullptr;
+    float4* d_cube_cells = nullptr;
     int cube_res = 0;
     uint8_t* d_shape_raw = nullptr;
     float* d_shape_pad = nullptr;
+    float4* d_shape_cells = nullptr;
     int nx = 0, ny = 0, nz = 0;
     uint8_t* d_blue = nullptr;
     int bn_w = 0, bn_h = 0;
@@ -87,9 +89,9 @@ DeviceTextures textures_of(const b200atmo_ctx* ctx) {
     DeviceTextures t;
     t.lut_pad = ctx->d_lut_pad;
     t.lut_cells = ctx->d_lut_cells;
-    t.cube_pad = ctx->d_cube_pad;
+    t.cube_cells = ctx->d_cube_cells;
     t.cube_res = ctx->cube_res;
-    t.shape_pad = ctx->d_shape_pad;
+    t.shape_cells = ctx->d_shape_cells;
     t.nx = ctx->nx;
     t.ny = ctx->ny;
     t.nz = ctx->nz;
@@ -114,19 +116,23 @@ int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_
     const size_t raw = size_t(6) * res * res, pad = size_t(6) * (res + 2) * (res + 2);
     uint8_t *d_raw = nullptr, *d_pad8 = nullptr;
     float* d_pad = nullptr;
+    float4* d_cells = nullptr;
     CU_TRY(ctx, cudaMalloc(&d_raw, raw));
     CU_TRY(ctx, cudaMalloc(&d_pad8, pad));
     CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
+    CU_TRY(ctx, cudaMalloc(&d_cells, size_t(6) * (res + 1) * (res + 1) * sizeof(float4)));
     CU_TRY(ctx, cudaMemcpyAsync(d_raw, h_faces6, raw, cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, launch_cube_pad(d_raw, res, d_pad8, d_pad, s));
-    ctx->launches++;
+    CU_TRY(ctx, launch_cube_pad(d_raw, res, d_pad8, d_pad, d_cells, s));
+    ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
     cudaFree(ctx->d_cube_raw);
     cudaFree(ctx->d_cube_pad_u8);
     cudaFree(ctx->d_cube_pad);
+    cudaFree(ctx->d_cube_cells);
     ctx->d_cube_raw = d_raw;
     ctx->d_cube_pad_u8 = d_pad8;
     ctx->d_cube_pad = d_pad;
+    ctx->d_cube_cells = d_cells;
     ctx->cube_res = res;
     return B200ATMO_OK;
 }
@@ -135,16 +141,20 @@ int upload_shape(b200atmo_ctx* ctx, const uint8_t* h, int nx, int ny, int nz, cu
     const size_t raw = size_t(nx) * ny * nz, pad = size_t(nx + 2) * (ny + 2) * (nz + 2);
     uint8_t* d_raw = nullptr;
     float* d_pad = nullptr;
+    float4* d_cells = nullptr;
     CU_TRY(ctx, cudaMalloc(&d_raw, raw));
     CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
+    CU_TRY(ctx, cudaMalloc(&d_cells, size_t(nx + 1) * (ny + 1) * (nz + 1) * 2 * sizeof(float4)));
     CU_TRY(ctx, cudaMemcpyAsync(d_raw, h, raw, cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, launch_shape_pad(d_raw, nx, ny, nz, d_pad, s));
-    ctx->launches++;
+    CU_TRY(ctx, launch_shape_pad(d_raw, nx, ny, nz, d_pad, d_cells, s));
+    ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
     cudaFree(ctx->d_shape_raw);
     cudaFree(ctx->d_shape_pad);
+    cudaFree(ctx->d_shape_cells);
     ctx->d_shape_raw = d_raw;
     ctx->d_shape_pad = d_pad;
+    ctx->d_shape_cells = d_cells;
     ctx->nx = nx;
     ctx->ny = ny;
     ctx->nz = nz;
@@ -240,6 +250,8 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
     cudaFree(ctx->d_cube_raw);
     cudaFree(ctx->d_cube_pad_u8);
     cudaFree(ctx->d_cube_pad);
+    cudaFree(ctx->d_cube_cells);
+    cudaFree(ctx->d_shape_cells);
     cudaFree(ctx->d_shape_raw);
     cudaFree(ctx->d_shape_pad);
     cudaFree(ctx->d_blue);
@@ -303,8 +315,8 @@ int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w
 
 int b200atmo_upload_shape3d(b200atmo_ctx* ctx, const uint8_t* h_texels, int nx, int ny, int nz) {
     if (!ctx || !h_texels) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_shape3d: NULL argument");
-    if (nx < 1 || ny < 1 || nz < 1 || nx > 1024 || ny > 1024 || nz > 1024)
-        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_shape3d: each dimension must be in [1, 1024]");
+    if (nx < 1 || ny < 1 || nz < 1 || nx > 512 || ny > 512 || nz > 512)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_shape3d: each dimension must be in [1, 512]");
     DeviceGuard g(ctx->device);
     return upload_shape(ctx, h_texels, nx, ny, nz, ctx->streams[0]);
 }

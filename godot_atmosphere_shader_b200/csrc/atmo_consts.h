@@ -20,9 +20,9 @@ struct Variant {
 struct DeviceTextures {
     const float* lut_pad = nullptr;
     const float4* lut_cells = nullptr;
-    const float* cube_pad = nullptr;
+    const float4* cube_cells = nullptr;
     int cube_res = 0;
-    const float* shape_pad = nullptr;
+    const float4* shape_cells = nullptr;
     int nx = 0, ny = 0, nz = 0;
     const uint8_t* blue_noise = nullptr;
     int bn_w = 0, bn_h = 0;
@@ -85,9 +85,9 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
         c.march_hmax = c.cloud_top_h * 1.05f;                                    // :192
         c.light_reach = (c.cloud_top_h - c.cloud_bottom_h) * 0.15f;              // :108
     }
-    c.cube_pad = t.cube_pad;
+    c.cube_cells = t.cube_cells;
     c.cube_res = t.cube_res;
-    c.shape_pad = t.shape_pad;
+    c.shape_cells = t.shape_cells;
     c.shape_nx = t.nx;
     c.shape_ny = t.ny;
     c.shape_nz = t.nz;

@@ -161,8 +161,26 @@ B200_DEV float sample_lut(const float* __restrict__ lut_pad, float u, float v) {
     return lerp_fma(lerp_fma(t00, t10, fx), lerp_fma(t01, t11, fx), fy);
 }
 
+// ---- cell layouts of the two noise textures ------------------------------------------------------
+// Built once at upload (atmo_kernels.cu) from the padded fp32 copies. A cell holds the texels of one
+// interpolation footprint with the x-differences precomputed, so a fetch is 1 (cube) / 2 (3D) 16-byte loads and the
+// lerps a+(b-a)*t become fma(b-a, t, a) with the SAME fp32 value of (b-a): results are bit-identical to lerping the
+// raw texels.
+//   cube cell (f, yi, xi)      = (t00, t10-t00, t01, t11-t01)                        yi, xi in [0, res]
+//   shape cell (zi, yi, xi)[0] = (t000, t100-t000, t010, t110-t010)   [1] = same at z+1   indices in [0, n]
+B200_DEV float4 make_cube_cell(const float* __restrict__ cube_pad, int res, int f, int yi, int xi) {
+    const int pr = res + 2;
+    const float* p = cube_pad + (size_t(f) * pr + yi) * pr + xi;
+    return make_float4(p[0], p[1] - p[0], p[pr], p[pr + 1] - p[pr]);
+}
+B200_DEV float4 make_shape_cell(const float* __restrict__ shp, int nx, int ny, int zi, int yi, int xi) {
+    const int px = nx + 2, pxy = px * (ny + 2);
+    const float* p = shp + size_t(zi) * pxy + yi * px + xi;   // zi may already include the +1 of the second half
+    return make_float4(p[0], p[1] - p[0], p[px], p[px + 1] - p[px]);
+}
+
 // texture(u_cloud_coverage_cubemap, d).r — cloud_funcs:45 (seamless bilinear, LOD 0)
-B200_DEV float sample_cube(const float* __restrict__ cube, int res, float x, float y, float z) {
+B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, float y, float z) {
     const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
     int f;
     float sc, tc, ma;
@@ -174,45 +192,34 @@ B200_DEV float sample_cube(const float* __restrict__ cube, int res, float x, flo
     const float s = 0.5f * (div_refined(sc, ma, inv_ma) + 1.0f);
     const float t = 0.5f * (div_refined(tc, ma, inv_ma) + 1.0f);
     float fx, fy;
-    int xi = floor_frac(s * float(res) - 0.5f, fx) + 1;
-    int yi = floor_frac(t * float(res) - 0.5f, fy) + 1;
-    xi = min(max(xi, 0), res);  // NaN / rounding guards only: the coordinates are in range by construction
-    yi = min(max(yi, 0), res);
-    const int pr = res + 2;
-    const float* p = cube + (size_t(f) * pr + yi) * pr + xi;
-    const float t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + pr), t11 = __ldg(p + pr + 1);
-    return lerp_fma(lerp_fma(t00, t10, fx), lerp_fma(t01, t11, fx), fy);
+    const int xi = floor_frac(s * float(res) - 0.5f, fx) + 1;   // in [0, res] by construction (|sc|,|tc| <= ma)
+    const int yi = floor_frac(t * float(res) - 0.5f, fy) + 1;
+    const unsigned rc = unsigned(res + 1);
+    unsigned idx = (unsigned(f) * rc + unsigned(yi)) * rc + unsigned(xi);
+    idx = min(idx, 6u * rc * rc - 1u);                            // NaN guard only
+    const float4 q = ldg4(cells + idx);
+    const float c0 = fmaf(q.y, fx, q.x), c1 = fmaf(q.w, fx, q.z);
+    return lerp_fma(c0, c1, fy);
 }
 
 // texture(u_cloud_shape_texture, c).r — cloud_funcs:49 (repeat, trilinear, LOD 0)
-B200_DEV float sample_shape(const float* __restrict__ shp, int nx, int ny, int nz, float cx, float cy, float cz) {
+B200_DEV float sample_shape(const float4* __restrict__ cells, int nx, int ny, int nz, float cx, float cy, float cz) {
     cx = cx - floorf(cx);  // repeat: wrap to [0,1]
     cy = cy - floorf(cy);
     cz = cz - floorf(cz);
     float fx, fy, fz;
-    int xi = floor_frac(cx * float(nx) - 0.5f, fx) + 1;
-    int yi = floor_frac(cy * float(ny) - 0.5f, fy) + 1;
-    int zi = floor_frac(cz * float(nz) - 0.5f, fz) + 1;
-    xi = min(max(xi, 0), nx);
-    yi = min(max(yi, 0), ny);
-    zi = min(max(zi, 0), nz);
-    const int px = nx + 2, pxy = px * (ny + 2);
-    const float* p = shp + size_t(zi) * pxy + yi * px + xi;
-    const float c00 = lerp_fma(__ldg(p), __ldg(p + 1), fx);
-    const float c10 = lerp_fma(__ldg(p + px), __ldg(p + px + 1), fx);
-    const float c01 = lerp_fma(__ldg(p + pxy), __ldg(p + pxy + 1), fx);
-    const float c11 = lerp_fma(__ldg(p + pxy + px), __ldg(p + pxy + px + 1), fx);
+    const int xi = floor_frac(cx * float(nx) - 0.5f, fx) + 1;   // in [0, n] by construction
+    const int yi = floor_frac(cy * float(ny) - 0.5f, fy) + 1;
+    const int zi = floor_frac(cz * float(nz) - 0.5f, fz) + 1;
+    const unsigned cxn = unsigned(nx + 1), cyn = unsigned(ny + 1);
+    unsigned idx = (unsigned(zi) * cyn + unsigned(yi)) * cxn + unsigned(xi);
+    idx = min(idx, cxn * cyn * unsigned(nz + 1) - 1u);            // NaN guard only
+    const float4 a = ldg4(cells + 2u * idx), b = ldg4(cells + 2u * idx + 1u);
+    const float c00 = fmaf(a.y, fx, a.x), c10 = fmaf(a.w, fx, a.z);
+    const float c01 = fmaf(b.y, fx, b.x), c11 = fmaf(b.w, fx, b.z);
     return lerp_fma(lerp_fma(c00, c10, fy), lerp_fma(c01, c11, fy), fz);
 }
 
-// Bilinear LUT fetch for the scatter loop from the CELL layout (atmo_kernels.cu: lut_cells_kernel):
-//   cell(xi, yi) = float4(t00, t10 - t00, t01 - t00, (t11 - t01) - (t10 - t00))   for padded texels (xi..xi+1, yi..yi+1)
-// so texture(LUT, uv) = t00 + dx*fx + fy*(dy + dxy*fx): ONE 16-byte load and three FMAs.
-// Inputs: mu = dot(up, sun_dir) in [-1,1]; y = 1 - height_ratio in [0,1].
-// Padded texel coordinates: xp = u*256 - 0.5 + 1 = 128*mu + 128.5, yp = 256*(1-y) + 0.5. floor(xp) = rn(xp - 0.5) comes
-// out of ONE fma against the 1.5*2^23 constant (integer in the low mantissa bits), the fraction out of a second fma
-// with the integer part folded into the addend. The LUT is smooth, so (unlike the noise textures) its coordinates
-// need not reproduce the shader's rounding; the fused forms are at least as accurate.
 B200_DEV float4 make_lut_cell(const float* __restrict__ lut_pad, int xi, int yi) {
     const float* p = lut_pad + yi * kLutPad + xi;
     const float t00 = p[0], t10 = p[1], t01 = p[kLutPad], t11 = p[kLutPad + 1];
@@ -359,9 +366,9 @@ B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
     if (!(hc > 0.0f)) return 0.0f;
     const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;                         // u_cloud_coverage_rotation * p.xz :43, exact
     const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
-    float coverage = sample_cube(c.cube_pad, c.cube_res, cpx, p.y, cpz);       // :45
+    float coverage = sample_cube(c.cube_cells, c.cube_res, cpx, p.y, cpz);     // :45
     coverage = coverage - 0.25f * hr + c.coverage_bias;                        // :46
-    const float tex = sample_shape(c.shape_pad, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
+    const float tex = sample_shape(c.shape_cells, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
                                    p.y * c.shape_scale, p.z * c.shape_scale);
     float shape = mixf(0.5f, tex, c.shape_factor);                             // :48-50
     if (c.shape_invert) shape = 1.0f - shape;                                  // :57-59

@@ -48,9 +48,9 @@ struct DevConsts {
     float march_space, march_ground;     // cloud_funcs:186-190
     float march_hmin, march_hmax;        // cloud_funcs:191-192
     float light_reach;                   // (top-bottom)*0.15, cloud_funcs:108
-    const float* cube_pad;               // [6][res+2][res+2] fp32 (= u8/255), seamless apron
+    const float4* cube_cells;            // [6][res+1][res+1] bilinear footprints of the seamless padded faces (u8/255 as fp32)
     int cube_res;
-    const float* shape_pad;              // [nz+2][ny+2][nx+2] fp32 (= u8/255), repeat apron
+    const float4* shape_cells;           // [nz+1][ny+1][nx+1][2] trilinear footprints of the repeat-padded volume
     int shape_nx, shape_ny, shape_nz;
     // --- variant ---
     int scatter_steps, cloud_steps;
@@ -76,8 +76,8 @@ struct RayIO {
 #ifdef __CUDACC__
 // kernels (atmo_kernels.cu)
 cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, float4* d_lut_cells, cudaStream_t s);
-cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, cudaStream_t s);
-cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, cudaStream_t s);
+cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, float4* d_cells, cudaStream_t s);
+cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, float4* d_cells, cudaStream_t s);
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);

@@ -116,10 +116,21 @@ __global__ void cube_pad_kernel(const uint8_t* __restrict__ faces, int res, uint
     }
 }
 
-cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, cudaStream_t s) {
+__global__ void cube_cells_kernel(const float* __restrict__ padded_f32, int res, float4* __restrict__ cells) {
+    const int rc = res + 1;
+    const size_t total = size_t(6) * rc * rc;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int f = int(idx / (size_t(rc) * rc)), rem = int(idx % (size_t(rc) * rc));
+        cells[idx] = make_cube_cell(padded_f32, res, f, rem / rc, rem % rc);
+    }
+}
+
+cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, float4* d_cells,
+                            cudaStream_t s) {
     const size_t total = size_t(6) * (res + 2) * (res + 2);
     const int blocks = int((total + 255) / 256);
     cube_pad_kernel<<<blocks > 4096 ? 4096 : blocks, 256, 0, s>>>(d_faces, res, d_padded, d_padded_f32);
+    cube_cells_kernel<<<blocks > 4096 ? 4096 : blocks, 256, 0, s>>>(d_padded_f32, res, d_cells);
     return cudaGetLastError();
 }
 
@@ -134,10 +145,21 @@ __global__ void shape_pad_kernel(const uint8_t* __restrict__ src, int nx, int ny
     }
 }
 
-cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, cudaStream_t s) {
+__global__ void shape_cells_kernel(const float* __restrict__ padded, int nx, int ny, int nz, float4* __restrict__ cells) {
+    const int cx = nx + 1, cy = ny + 1;
+    const size_t total = size_t(cx) * cy * (nz + 1);
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int xi = int(idx % cx), yi = int((idx / cx) % cy), zi = int(idx / (size_t(cx) * cy));
+        cells[2 * idx] = make_shape_cell(padded, nx, ny, zi, yi, xi);
+        cells[2 * idx + 1] = make_shape_cell(padded, nx, ny, zi + 1, yi, xi);
+    }
+}
+
+cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, float4* d_cells, cudaStream_t s) {
     const size_t total = size_t(nx + 2) * (ny + 2) * (nz + 2);
     const int blocks = int((total + 255) / 256);
     shape_pad_kernel<<<blocks > 8192 ? 8192 : blocks, 256, 0, s>>>(d_src, nx, ny, nz, d_dst);
+    shape_cells_kernel<<<blocks > 8192 ? 8192 : blocks, 256, 0, s>>>(d_dst, nx, ny, nz, d_cells);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ typedef struct HostsimTextures {
 }  // extern "C"
 
 #include <vector>
-static std::vector<float4> g_cells;  // host restatement of lut_cells_kernel (single-threaded test helper)
+static std::vector<float4> g_cells, g_cube, g_shape;  // host restatement of lut_cells_kernel (single-threaded test helper)
 static DeviceTextures tex_of(const HostsimTextures* t) {
     DeviceTextures d;
     d.lut_pad = t->lut_pad;
@@ -31,9 +31,25 @@ static DeviceTextures tex_of(const HostsimTextures* t) {
     for (int yi = 0; yi < kLutCells; ++yi)
         for (int xi = 0; xi < kLutCells; ++xi) g_cells[size_t(yi) * kLutCells + xi] = make_lut_cell(t->lut_pad, xi, yi);
     d.lut_cells = g_cells.data();
-    d.cube_pad = t->cube_pad;
+    {   // host restatement of cube_cells_kernel / shape_cells_kernel
+        const int res = t->cube_res, rc = res + 1;
+        g_cube.resize(size_t(6) * rc * rc);
+        for (int f = 0; f < 6; ++f)
+            for (int yi = 0; yi < rc; ++yi)
+                for (int xi = 0; xi < rc; ++xi) g_cube[(size_t(f) * rc + yi) * rc + xi] = make_cube_cell(t->cube_pad, res, f, yi, xi);
+        const int cx = t->nx + 1, cy = t->ny + 1, cz = t->nz + 1;
+        g_shape.resize(size_t(cx) * cy * cz * 2);
+        for (int zi = 0; zi < cz; ++zi)
+            for (int yi = 0; yi < cy; ++yi)
+                for (int xi = 0; xi < cx; ++xi) {
+                    const size_t idx = (size_t(zi) * cy + yi) * cx + xi;
+                    g_shape[2 * idx] = make_shape_cell(t->shape_pad, t->nx, t->ny, zi, yi, xi);
+                    g_shape[2 * idx + 1] = make_shape_cell(t->shape_pad, t->nx, t->ny, zi + 1, yi, xi);
+                }
+    }
+    d.cube_cells = g_cube.data();
     d.cube_res = t->cube_res;
-    d.shape_pad = t->shape_pad;
+    d.shape_cells = g_shape.data();
     d.nx = t->nx; d.ny = t->ny; d.nz = t->nz;
     d.blue_noise = t->blue_noise;
     d.bn_w = t->bn_w; d.bn_h = t->bn_h;

@@ -77,6 +77,13 @@ class B200AtmoCamera(C.Structure):
     ]
 
 
+class B200AtmoNoise(C.Structure):
+    """Subset of FastNoiseLite's properties used by the generator (include/b200atmo.h)."""
+
+    _fields_ = [("seed", C.c_int32), ("frequency", C.c_float), ("octaves", C.c_int32), ("lacunarity", C.c_float),
+                ("gain", C.c_float)]
+
+
 IDENTITY16 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0)
 
 

@@ -20,7 +20,7 @@ _lib = None
 EXPORTS = [
     "b200atmo_version", "b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera", "b200atmo_create",
     "b200atmo_destroy", "b200atmo_last_error", "b200atmo_default_params", "b200atmo_set_params", "b200atmo_get_params",
-    "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube",
+    "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube", "b200atmo_generate_noise_cubemap",
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_make_rays", "b200atmo_render_frame_host",
     "b200atmo_launch_count",
@@ -58,6 +58,7 @@ def lib():
         L.b200atmo_upload_blue_noise.argtypes = [vp, vp, i32, i32]
         L.b200atmo_upload_shape3d.argtypes = [vp, vp, i32, i32, i32]
         L.b200atmo_upload_coverage_cube.argtypes = [vp, vp, i32]
+        L.b200atmo_generate_noise_cubemap.argtypes = [vp, C.POINTER(abi.B200AtmoNoise), i32, C.POINTER(C.c_float), vp, i32]
         L.b200atmo_bake_optical_depth.argtypes = [vp, vp]
         L.b200atmo_download_lut.argtypes = [vp, vp]
         L.b200atmo_download_cube_padded.argtypes = [vp, vp, sz, C.POINTER(i32)]
@@ -146,6 +147,17 @@ class AtmosphereContext:
         assert t.ndim == 3 and t.shape[0] == 6 and t.shape[1] == t.shape[2]
         self._check(lib().b200atmo_upload_coverage_cube(self._h, t.ctypes.data, t.shape[1]))
         self._cube_res = int(t.shape[1])
+
+    def generate_noise_cubemap(self, noise: "abi.B200AtmoNoise", res: int, scale=(100.0, 100.0, 100.0), download=True,
+                               set_as_coverage=False):
+        """NoiseCubemap._generate_images on the device; returns the 6 x res x res u8 faces if `download`."""
+        out = np.empty((6, res, res), dtype=np.uint8) if download else None
+        sc = (C.c_float * 3)(*[float(v) for v in scale])
+        self._check(lib().b200atmo_generate_noise_cubemap(self._h, C.byref(noise), int(res), sc,
+                                                          out.ctypes.data if download else None, 1 if set_as_coverage else 0))
+        if set_as_coverage:
+            self._cube_res = int(res)
+        return out
 
     # ---- LUT ----
     def bake_optical_depth(self, stream=None):

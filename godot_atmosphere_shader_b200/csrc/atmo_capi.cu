@@ -112,7 +112,8 @@ int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
     return B200ATMO_OK;
 }
 
-int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_t s) {
+// installs a cube whose raw faces are either on the host (h_faces6) or already on the device (d_src)
+int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_t s, const uint8_t* d_src = nullptr) {
     const size_t raw = size_t(6) * res * res, pad = size_t(6) * (res + 2) * (res + 2);
     uint8_t *d_raw = nullptr, *d_pad8 = nullptr;
     float* d_pad = nullptr;
@@ -121,7 +122,7 @@ int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_
     CU_TRY(ctx, cudaMalloc(&d_pad8, pad));
     CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
     CU_TRY(ctx, cudaMalloc(&d_cells, size_t(6) * (res + 1) * (res + 1) * sizeof(float4)));
-    CU_TRY(ctx, cudaMemcpyAsync(d_raw, h_faces6, raw, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw, d_src ? d_src : h_faces6, raw, d_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, launch_cube_pad(d_raw, res, d_pad8, d_pad, d_cells, s));
     ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
@@ -327,6 +328,27 @@ int b200atmo_upload_coverage_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, in
         return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_coverage_cube: res must be in [1, 4096]");
     DeviceGuard g(ctx->device);
     return upload_cube(ctx, h_faces6, res, ctx->streams[0]);
+}
+
+int b200atmo_generate_noise_cubemap(b200atmo_ctx* ctx, const B200AtmoNoise* noise, int res, const float scale[3],
+                                    uint8_t* h_faces6_out, int set_as_coverage) {
+    if (!ctx || !noise || !scale) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_generate_noise_cubemap: NULL argument");
+    if (res < 1 || res > 4096) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_generate_noise_cubemap: res must be in [1, 4096]");
+    if (noise->octaves < 1 || noise->octaves > 32) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_generate_noise_cubemap: octaves must be in [1, 32]");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->streams[0];
+    const size_t raw = size_t(6) * res * res;
+    uint8_t* d_faces = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d_faces, raw));
+    cudaError_t e = launch_noise_cube(*noise, scale, res, d_faces, s);
+    ctx->launches++;
+    if (e == cudaSuccess && h_faces6_out) e = cudaMemcpyAsync(h_faces6_out, d_faces, raw, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    int rc = B200ATMO_OK;
+    if (e != cudaSuccess) rc = fail(ctx, B200ATMO_E_CUDA, std::string("noise cubemap: ") + cudaGetErrorString(e));
+    else if (set_as_coverage) rc = upload_cube(ctx, nullptr, res, s, d_faces);
+    cudaFree(d_faces);
+    return rc;
 }
 
 int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream) {

@@ -478,6 +478,80 @@ template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px,
 }
 
 // ------------------------------------------------------------------------------------------------
+// NoiseCubemap content: "b200 gradient fBm v1" (see include/b200atmo.h). Exact arithmetic throughout (no fmaf), so the
+// bytes are identical on every IEEE machine.
+// ------------------------------------------------------------------------------------------------
+B200_DEV unsigned noise_hash(int ix, int iy, int iz, unsigned seed) {
+    unsigned h = seed;
+    h ^= unsigned(ix) * 0x8da6b343u;
+    h ^= unsigned(iy) * 0xd8163841u;
+    h ^= unsigned(iz) * 0xcb1ab31fu;
+    h *= 0x9e3779b1u;
+    h ^= h >> 15;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    return h;
+}
+B200_DEV float noise_grad(unsigned hash, float x, float y, float z) {
+    const unsigned h = hash & 15u;
+    const float u = h < 8u ? x : y;
+    const float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+    return ((h & 1u) ? -u : u) + ((h & 2u) ? -v : v);
+}
+B200_DEV float noise_fade(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+B200_DEV float noise_lerp(float a, float b, float t) { return a + (b - a) * t; }
+B200_DEV float noise3(float x, float y, float z, unsigned seed) {
+    const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+    const int ix = int(fx0), iy = int(fy0), iz = int(fz0);
+    const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+    const float u = noise_fade(fx), v = noise_fade(fy), w = noise_fade(fz);
+    const float n000 = noise_grad(noise_hash(ix, iy, iz, seed), fx, fy, fz);
+    const float n100 = noise_grad(noise_hash(ix + 1, iy, iz, seed), fx - 1.0f, fy, fz);
+    const float n010 = noise_grad(noise_hash(ix, iy + 1, iz, seed), fx, fy - 1.0f, fz);
+    const float n110 = noise_grad(noise_hash(ix + 1, iy + 1, iz, seed), fx - 1.0f, fy - 1.0f, fz);
+    const float n001 = noise_grad(noise_hash(ix, iy, iz + 1, seed), fx, fy, fz - 1.0f);
+    const float n101 = noise_grad(noise_hash(ix + 1, iy, iz + 1, seed), fx - 1.0f, fy, fz - 1.0f);
+    const float n011 = noise_grad(noise_hash(ix, iy + 1, iz + 1, seed), fx, fy - 1.0f, fz - 1.0f);
+    const float n111 = noise_grad(noise_hash(ix + 1, iy + 1, iz + 1, seed), fx - 1.0f, fy - 1.0f, fz - 1.0f);
+    const float a = noise_lerp(noise_lerp(n000, n100, u), noise_lerp(n010, n110, u), v);
+    const float b = noise_lerp(noise_lerp(n001, n101, u), noise_lerp(n011, n111, u), v);
+    return noise_lerp(a, b, w);
+}
+// fractal sum normalised to about [-1, 1]
+B200_DEV float noise_fbm(float x, float y, float z, const B200AtmoNoise& n) {
+    float freq = n.frequency, amp = 1.0f, sum = 0.0f, norm = 0.0f;
+    for (int o = 0; o < n.octaves; ++o) {
+        sum = sum + amp * noise3(x * freq, y * freq, z * freq, unsigned(n.seed) + unsigned(o) * 0x632be5abu);
+        norm = norm + amp;
+        freq = freq * n.lacunarity;
+        amp = amp * n.gain;
+    }
+    return sum / norm;
+}
+// One texel of NoiseCubemap._generate_images (noise_cubemap.gd:108-134)
+B200_DEV unsigned char noise_cube_texel(int side, int x, int y, int res, const float scale[3], const B200AtmoNoise& n) {
+    const float half = 0.5f * float(res);                                         // half_resolution_2d, :102
+    const float px = (float(x) + 0.5f) / half - 1.0f;                             // :110-111
+    const float py = (float(res - y - 1) + 0.5f) / half - 1.0f;
+    f3 pos = mk3(1.0f, py, -px);                                                  // :113, then .normalized()
+    const float l = sqrtf(dot3(pos, pos));
+    pos = mk3(pos.x / l, pos.y / l, pos.z / l);
+    f3 q;
+    switch (side) {                                                               // :116-128
+        case 0: q = mk3(pos.x, pos.y, pos.z); break;
+        case 1: q = mk3(-pos.x, pos.y, -pos.z); break;
+        case 2: q = mk3(-pos.z, pos.x, -pos.y); break;
+        case 3: q = mk3(-pos.z, -pos.x, pos.y); break;
+        case 4: q = mk3(-pos.z, pos.y, pos.x); break;
+        default: q = mk3(pos.z, pos.y, -pos.x); break;
+    }
+    const float density = 0.5f + 0.5f * noise_fbm(q.x * scale[0], q.y * scale[1], q.z * scale[2], n);   // :130
+    // Image.set_pixel on FORMAT_L8: uint8(CLAMP(v * 255.0, 0, 255)) (engine behaviour)
+    const float v = fminf(fmaxf(density * 255.0f, 0.0f), 255.0f);
+    return (unsigned char)(int(v));
+}
+
+// ------------------------------------------------------------------------------------------------
 // include/planet_atmosphere_main.gdshaderinc:144-196 — one fragment, ray already generated
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int LIGHT> B200_DEV bool shade_ray(const DevConsts& c, f3 o, f3 d, float linear_depth, float jitter, float4& out) {

@@ -78,6 +78,7 @@ struct RayIO {
 cudaError_t launch_bake_lut(float R, float H, float rho, float* d_lut, float* d_lut_pad, float4* d_lut_cells, cudaStream_t s);
 cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, float* d_padded_f32, float4* d_cells, cudaStream_t s);
 cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, float4* d_cells, cudaStream_t s);
+cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], int res, uint8_t* d_faces, cudaStream_t s);
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);

@@ -163,6 +163,31 @@ cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float
     return cudaGetLastError();
 }
 
+// NoiseCubemap._generate_images (noise_cubemap.gd:101-140) on the device: one thread per texel.
+struct NoiseCubeArgs {
+    B200AtmoNoise noise;
+    float scale[3];
+    int res;
+};
+__global__ void __launch_bounds__(256) noise_cube_kernel(const __grid_constant__ NoiseCubeArgs a, uint8_t* __restrict__ faces) {
+    const size_t total = size_t(6) * a.res * a.res;
+    for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const int side = int(idx / (size_t(a.res) * a.res)), rem = int(idx % (size_t(a.res) * a.res));
+        faces[idx] = noise_cube_texel(side, rem % a.res, rem / a.res, a.res, a.scale, a.noise);
+    }
+}
+
+cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], int res, uint8_t* d_faces, cudaStream_t s) {
+    NoiseCubeArgs a;
+    a.noise = noise;
+    for (int k = 0; k < 3; ++k) a.scale[k] = scale[k];
+    a.res = res;
+    const size_t total = size_t(6) * res * res;
+    const size_t blocks = (total + 255) / 256;
+    noise_cube_kernel<<<unsigned(blocks > 148 * 64 ? 148 * 64 : blocks), 256, 0, s>>>(a, d_faces);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // render kernels
 // ------------------------------------------------------------------------------------------------

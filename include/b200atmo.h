@@ -153,6 +153,26 @@ int b200atmo_upload_shape3d(b200atmo_ctx* ctx, const uint8_t* h_texels, int nx, 
  * +X,-X,+Y,-Y,+Z,-Z (noise_cubemap.gd:116-128), row 0 = top. Seamless bilinear, LOD 0. */
 int b200atmo_upload_coverage_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res);
 
+/* ---- NoiseCubemap generator (replaces NoiseCubemap._generate_images, noise_cubemap.gd:101-140) ------ */
+/*
+ * The reference evaluates a Godot `Noise` (FastNoiseLite, engine code outside the addon) at 6*res*res texel
+ * directions in a GDScript loop ("This is really slow", noise_cubemap.gd:100). The engine's noise is not part of
+ * the reference tree, so the CONTENT is defined here ("b200 gradient fBm v1": hashed 3D gradient noise, quintic
+ * fade, `octaves` octaves); the texel -> direction mapping, the `* scale`, density = 0.5 + 0.5*noise and the L8
+ * quantisation follow noise_cubemap.gd:110-134 exactly. Face order +X,-X,+Y,-Y,+Z,-Z, row 0 = top.
+ */
+typedef struct B200AtmoNoise {
+    int32_t seed;        /* FastNoiseLite.seed */
+    float frequency;     /* FastNoiseLite.frequency (default 0.01) */
+    int32_t octaves;     /* fractal_octaves (>= 1) */
+    float lacunarity;    /* fractal_lacunarity (2.0) */
+    float gain;          /* fractal_gain (0.5) */
+} B200AtmoNoise;
+/* Generates on the device. h_faces6_out (6*res*res bytes) may be NULL; set_as_coverage != 0 also installs the result
+ * as u_cloud_coverage_cubemap (device to device). res in [1, 4096] (noise_cubemap.gd:30). */
+int b200atmo_generate_noise_cubemap(b200atmo_ctx* ctx, const B200AtmoNoise* noise, int res, const float scale[3],
+                                    uint8_t* h_faces6_out, int set_as_coverage);
+
 /* ---- optical-depth LUT (replaces OpticalDepthBaker, optical_depth_baker.gd:37-85) -------------- */
 #define B200ATMO_LUT_SIZE 256
 int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream);

@@ -288,6 +288,11 @@ void oracle_compute_atmosphere_v2_f32(const B200AtmoParams* p, const float* lut,
                                           vec3<float>{sun_dir[0], sun_dir[1], sun_dir[2]}, jitter);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
+void oracle_noise_cubemap(const B200AtmoNoise* noise, int res, const float scale[3], uint8_t* out) {
+    noisegen::generate_images(*noise, res, scale, out);
+}
+float oracle_noise3(float x, float y, float z, uint32_t seed) { return noisegen::noise3(x, y, z, seed); }
+void oracle_cubemap_atlas(const uint8_t* faces, int res, uint8_t* atlas) { noisegen::importable_image(faces, res, atlas); }
 void oracle_encode_float(float h, uint8_t out[4]) { encode_float_to_viewport(h, out); }
 float oracle_decode_float(const uint8_t in[4]) { return decode_viewport_bytes(in); }
 

@@ -733,4 +733,90 @@ inline void fragment_make_ray(mat4<T> inv_projection_matrix, mat4<T> inv_view_ma
     *ray_dir = normalize(vec3<T>{view_coords.x, view_coords.y, view_coords.z} - *ray_origin);
 }
 
+// ------------------------------------------------------------------------------------------------
+// NoiseCubemap._generate_images — noise_cubemap.gd:101-140.
+// The noise itself (`noise.get_noise_3dv`, Godot's FastNoiseLite) is engine code outside the reference tree: its
+// content is DEFINED by this repo's include/b200atmo.h ("b200 gradient fBm v1"); what follows the reference is the
+// texel -> direction mapping (:110-128), `pos * scale`, density = 0.5 + 0.5*n (:130) and the L8 store (:134).
+// fp32 only (the generator's output is bytes; parity is bit-exact).
+// ------------------------------------------------------------------------------------------------
+namespace noisegen {
+inline uint32_t hash3(int32_t ix, int32_t iy, int32_t iz, uint32_t seed) {
+    uint32_t h = seed;
+    h ^= uint32_t(ix) * 0x8da6b343u;
+    h ^= uint32_t(iy) * 0xd8163841u;
+    h ^= uint32_t(iz) * 0xcb1ab31fu;
+    h *= 0x9e3779b1u;
+    h ^= h >> 15;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    return h;
+}
+inline float grad(uint32_t hash, float x, float y, float z) {  // Perlin's 12 edge directions (+4 repeats)
+    const uint32_t h = hash & 15u;
+    const float u = h < 8u ? x : y;
+    const float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+    return ((h & 1u) ? -u : u) + ((h & 2u) ? -v : v);
+}
+inline float fade(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+inline float lerp(float a, float b, float t) { return a + (b - a) * t; }
+inline float noise3(float x, float y, float z, uint32_t seed) {
+    const float x0 = std::floor(x), y0 = std::floor(y), z0 = std::floor(z);
+    const int32_t ix = int32_t(x0), iy = int32_t(y0), iz = int32_t(z0);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    const float u = fade(fx), v = fade(fy), w = fade(fz);
+    float c[2][2][2];
+    for (int dz = 0; dz < 2; ++dz)
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+                c[dz][dy][dx] = grad(hash3(ix + dx, iy + dy, iz + dz, seed), fx - float(dx), fy - float(dy), fz - float(dz));
+    const float a = lerp(lerp(c[0][0][0], c[0][0][1], u), lerp(c[0][1][0], c[0][1][1], u), v);
+    const float b = lerp(lerp(c[1][0][0], c[1][0][1], u), lerp(c[1][1][0], c[1][1][1], u), v);
+    return lerp(a, b, w);
+}
+inline float fbm(float x, float y, float z, const B200AtmoNoise& n) {
+    float freq = n.frequency, amp = 1.0f, sum = 0.0f, norm = 0.0f;
+    for (int o = 0; o < n.octaves; ++o) {
+        sum = sum + amp * noise3(x * freq, y * freq, z * freq, uint32_t(n.seed) + uint32_t(o) * 0x632be5abu);
+        norm = norm + amp;
+        freq = freq * n.lacunarity;
+        amp = amp * n.gain;
+    }
+    return sum / norm;
+}
+// noise_cubemap.gd:101-140 (without the mipmaps: LOD 0 only)
+inline void generate_images(const B200AtmoNoise& noise, int resolution, const float scale[3], uint8_t* out) {
+    const float half = 0.5f * float(resolution);  // half_resolution_2d
+    for (int side = 0; side < 6; ++side)
+        for (int y = 0; y < resolution; ++y)
+            for (int x = 0; x < resolution; ++x) {
+                const float p2x = (float(x) + 0.5f) / half - 1.0f;
+                const float p2y = (float(resolution - y - 1) + 0.5f) / half - 1.0f;
+                vec3<float> pos = normalize(vec3<float>{1.0f, p2y, -p2x});  // +X
+                switch (side) {
+                    case 0: pos = {pos.x, pos.y, pos.z}; break;
+                    case 1: pos = {-pos.x, pos.y, -pos.z}; break;
+                    case 2: pos = {-pos.z, pos.x, -pos.y}; break;
+                    case 3: pos = {-pos.z, -pos.x, pos.y}; break;
+                    case 4: pos = {-pos.z, pos.y, pos.x}; break;
+                    case 5: pos = {pos.z, pos.y, -pos.x}; break;
+                }
+                const float density = 0.5f + 0.5f * fbm(pos.x * scale[0], pos.y * scale[1], pos.z * scale[2], noise);
+                // Image.set_pixel(x, y, Color(d,d,d)) on FORMAT_L8: uint8(CLAMP(v*255, 0, 255))
+                const float v = std::min(std::max(density * 255.0f, 0.0f), 255.0f);
+                out[(size_t(side) * resolution + y) * resolution + x] = uint8_t(int(v));
+            }
+}
+// NoiseCubemap._generate_importable_image (noise_cubemap.gd:143-155): 3 x 2 atlas, side = x + 3*y
+inline void importable_image(const uint8_t* faces, int res, uint8_t* atlas) {
+    const int count_x = 3, count_y = 2;
+    for (int ay = 0; ay < count_y; ++ay)
+        for (int ax = 0; ax < count_x; ++ax) {
+            const int side = ax + ay * count_x;
+            for (int y = 0; y < res; ++y)
+                std::memcpy(atlas + (size_t(ay * res + y) * count_x + ax) * res, faces + (size_t(side) * res + y) * res, size_t(res));
+        }
+}
+}  // namespace noisegen
+
 }  // namespace oracle

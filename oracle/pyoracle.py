@@ -227,6 +227,24 @@ def compute_atmosphere_v2(params, lut, steps, origin, direction, planet_center, 
     return tuple(float(x) for x in out)
 
 
+def noise_cubemap(noise, res: int, scale=(100.0, 100.0, 100.0)) -> np.ndarray:
+    out = np.empty((6, res, res), dtype=np.uint8)
+    lib().oracle_noise_cubemap(C.byref(noise), C.c_int(res), (C.c_float * 3)(*[float(v) for v in scale]), _ptr(out))
+    return out
+
+
+def noise3(x, y, z, seed=0) -> float:
+    lib().oracle_noise3.restype = C.c_float
+    return float(lib().oracle_noise3(C.c_float(x), C.c_float(y), C.c_float(z), C.c_uint32(seed)))
+
+
+def cubemap_atlas(faces: np.ndarray) -> np.ndarray:
+    res = int(faces.shape[1])
+    out = np.empty((2 * res, 3 * res), dtype=np.uint8)
+    lib().oracle_cubemap_atlas(_ptr(np.ascontiguousarray(faces)), C.c_int(res), _ptr(out))
+    return out
+
+
 def encode_float(h: float):
     out = (C.c_uint8 * 4)()
     lib().oracle_encode_float(C.c_float(h), out)

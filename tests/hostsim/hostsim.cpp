@@ -113,6 +113,12 @@ void hostsim_make_rays(const B200AtmoParams* p, const B200AtmoCamera* cam, const
     }
 }
 
+void hostsim_noise_cubemap(const B200AtmoNoise* noise, int res, const float scale[3], uint8_t* out) {
+    for (int side = 0; side < 6; ++side)
+        for (int y = 0; y < res; ++y)
+            for (int x = 0; x < res; ++x) out[(size_t(side) * res + y) * res + x] = noise_cube_texel(side, x, y, res, scale, *noise);
+}
+
 float hostsim_sqrt_refined(float x) { float inv; return sqrt_refined(x, inv); }
 float hostsim_div_refined(float a, float b) { return div_refined(a, b, 1.0f / b); }
 int hostsim_floor_frac(float x, float* frac) { return floor_frac(x, *frac); }

@@ -73,7 +73,7 @@ class B200AtmoCamera(C.Structure):
         ("view", C.c_float * 16),
         ("model", C.c_float * 16),
         ("double_precision", C.c_int32),
-        ("reserved", C.c_int32),
+        ("clip_box_size", C.c_float),
     ]
 
 

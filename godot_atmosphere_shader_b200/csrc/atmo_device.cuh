@@ -574,6 +574,27 @@ template <int MODEL, int LIGHT> B200_DEV bool shade_ray(const DevConsts& c, f3 o
     return false;
 }
 
+// MODE_FAR coverage (planet_atmosphere.gd:261-282,302-321): the node draws a BoxMesh of edge `atmo_clip_distance`
+// centred on itself, so the fragment shader only runs where that cube's front faces are rasterised and pass the
+// depth test. Restated with the reference's own (unused) slab test, include/util.gdshaderinc:5-17, in model space:
+// a point o + t*d keeps its parameter t under the affine view->model map, so tN is comparable with linear_depth.
+// min/max have IEEE fmin/fmax semantics (NaN operands ignored: axis-parallel rays produce 0*inf), as in the oracle.
+B200_DEV float sel_max(float a, float b) { return fmaxf(a, b); }
+B200_DEV float sel_min(float a, float b) { return fminf(a, b); }
+B200_DEV bool far_box_covers(const DevConsts& c, f3 o, f3 d, float linear_depth) {
+    float om[4], dm[4];
+    mat4_mul(c.v2m, o.x, o.y, o.z, 1.0f, om);
+    mat4_mul(c.v2m, d.x, d.y, d.z, 0.0f, dm);
+    const float bs = c.clip_box_half;
+    const float mx = 1.0f / dm[0], my = 1.0f / dm[1], mz = 1.0f / dm[2];       // util:6
+    const float nx = mx * om[0], ny = my * om[1], nz = mz * om[2];            // util:7
+    const float kx = fabsf(mx) * bs, ky = fabsf(my) * bs, kz = fabsf(mz) * bs; // util:8
+    const float tN = sel_max(sel_max(-nx - kx, -ny - ky), -nz - kz);           // util:9-11
+    const float tF = sel_min(sel_min(-nx + kx, -ny + ky), -nz + kz);           // util:10-12
+    if (tN > tF || tF < 0.0f) return false;                                    // util:13-15
+    return tN > 0.0f && tN < linear_depth;  // front faces in front of the camera, nearer than the opaque depth
+}
+
 // main:128-142 — ray generation from the depth texture (exact arithmetic, shader op order)
 B200_DEV void make_ray(const DevConsts& c, int x, int y, float nonlinear_depth, f3& o, f3& d, float& linear_depth, float& jitter) {
     const float su = (float(x) + 0.5f) / float(c.fw), sv = (float(y) + 0.5f) / float(c.fh);  // SCREEN_UV

@@ -60,6 +60,7 @@ struct DevConsts {
     const uint8_t* blue_noise;
     int bn_w, bn_h;
     int fw, fh, row_begin, row_end;
+    float clip_box_half;                   // MODE_FAR proxy cube half edge (0 = fullscreen)
 };
 
 struct RayIO {

@@ -218,8 +218,10 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
     f3 o, d;
     float linear_depth, jitter;
     make_ray(c, x, y, __ldcs(io.depth + i), o, d, linear_depth, jitter);
-    float4 out;
-    const bool disc = shade_ray<MODEL, LIGHT>(c, o, d, linear_depth, jitter, out);
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool disc = true;
+    if (!(c.clip_box_half > 0.0f) || far_box_covers(c, o, d, linear_depth))  // MODE_FAR: outside the proxy cube = not rasterised
+        disc = shade_ray<MODEL, LIGHT>(c, o, d, linear_depth, jitter, out);
     __stcs(static_cast<float4*>(io.rgba) + i, out);
     if (io.discard) io.discard[i] = disc ? 1 : 0;
 }

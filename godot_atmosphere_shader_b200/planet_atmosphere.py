@@ -407,6 +407,8 @@ class PlanetAtmosphere:
         cam.view[:] = flat_colmajor(np.linalg.inv(np.asarray(inv_view, dtype=np.float64)) if view is None else view)
         cam.model[:] = flat_colmajor(self.global_transform)
         cam.double_precision = 1 if double_precision else 0
+        # MODE_FAR draws the resized BoxMesh (:314-321); MODE_NEAR the fullscreen quad (u_clip_mode, :268-275)
+        cam.clip_box_size = float(self._far_mesh_size) if self._mode == MODE_FAR else 0.0
         return cam
 
     def render(self, camera: abi.B200AtmoCamera, depth, width, height, rgba, discard=None, stream=None):

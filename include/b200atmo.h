@@ -115,7 +115,9 @@ typedef struct B200AtmoCamera {
     float view[16];                 /* VIEW_MATRIX */
     float model[16];                /* MODEL_MATRIX of the PlanetAtmosphere node */
     int32_t double_precision;       /* != 0: DOUBLE_PRECISION workaround, negate inv_view origin (main:118-125) */
-    int32_t reserved;
+    float clip_box_size;            /* MODE_FAR proxy mesh: edge of the BoxMesh centred on the node (planet_atmosphere.gd:302-321);
+                                       only pixels whose view ray enters that box in front of the opaque depth are shaded, the
+                                       rest are discarded like un-rasterised pixels. 0 = MODE_NEAR / fullscreen quad (u_clip_mode) */
 } B200AtmoCamera;
 
 typedef struct b200atmo_ctx b200atmo_ctx;

@@ -132,9 +132,11 @@ void render_frame(const B200AtmoParams* p, const OracleVariant* v, const B200Atm
             T jitter = T(0);
             if (tex && tex->blue_noise)
                 jitter = T(tex->blue_noise[size_t(y & (tex->bn_h - 1)) * tex->bn_w + (x & (tex->bn_w - 1))]) / T(255);
-            vec3<T> albedo;
-            T alpha;
-            bool disc = fragment_from_ray(u, var, o, d, linear_depth, jitter, pc, sc, inv_view_frag, &albedo, &alpha);
+            vec3<T> albedo = {T(0), T(0), T(0)};
+            T alpha = T(0);
+            bool disc = true;
+            if (!(cam->clip_box_size > 0.0f) || far_box_covers(u, inv_view_frag, T(cam->clip_box_size), o, d, linear_depth))
+                disc = fragment_from_ray(u, var, o, d, linear_depth, jitter, pc, sc, inv_view_frag, &albedo, &alpha);
             rgba[4 * i] = albedo.x;
             rgba[4 * i + 1] = albedo.y;
             rgba[4 * i + 2] = albedo.z;
@@ -233,6 +235,10 @@ void oracle_ray_sphere_f32(const float c[3], float r, const float o[3], const fl
 void oracle_ray_sphere_f64(const double c[3], double r, const double o[3], const double d[3], double out[2]) {
     vec2<double> rs = ray_sphere<double>({c[0], c[1], c[2]}, r, {o[0], o[1], o[2]}, {d[0], d[1], d[2]});
     out[0] = rs.x; out[1] = rs.y;
+}
+void oracle_ray_box_f32(const float ro[3], const float rd[3], const float box[3], float out[2]) {
+    vec2<float> r = ray_box_intersection<float>({ro[0], ro[1], ro[2]}, {rd[0], rd[1], rd[2]}, {box[0], box[1], box[2]});
+    out[0] = r.x; out[1] = r.y;
 }
 float oracle_atmosphere_density_f32(const B200AtmoParams* p, float height) {
     return get_atmosphere_density(make_uniforms<float>(*p), height);

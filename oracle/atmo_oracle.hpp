@@ -89,6 +89,23 @@ template <class T> inline mat4<T> load_mat4(const float* m) {
 }
 template <class T> inline vec3<T> load_vec3(const float* v) { return {T(v[0]), T(v[1]), T(v[2])}; }
 
+// include/util.gdshaderinc:5-17 — unused by the shipped shaders; used here to restate the MODE_FAR proxy-cube
+// coverage of the rasteriser (planet_atmosphere.gd:261-282,302-321). max/min with IEEE fmax/fmin semantics (a NaN
+// operand is ignored — what GPU min/max instructions do and what this routine relies on for axis-parallel rays).
+template <class T> inline T sel_max(T a, T b) { return std::fmax(a, b); }
+template <class T> inline T sel_min(T a, T b) { return std::fmin(a, b); }
+template <class T> inline vec2<T> ray_box_intersection(vec3<T> ro, vec3<T> rd, vec3<T> boxSize) {
+    vec3<T> m = {T(1) / rd.x, T(1) / rd.y, T(1) / rd.z};
+    vec3<T> n = m * ro;
+    vec3<T> k = vec3<T>{std::fabs(m.x), std::fabs(m.y), std::fabs(m.z)} * boxSize;
+    vec3<T> t1 = -n - k;
+    vec3<T> t2 = -n + k;
+    T tN = sel_max(sel_max(t1.x, t1.y), t1.z);
+    T tF = sel_min(sel_min(t2.x, t2.y), t2.z);
+    if (tN > tF || tF < T(0)) return {T(-1), T(-1)};
+    return {tN, tF};
+}
+
 // include/util.gdshaderinc:49-59
 template <class T> inline T pow4(T x) { return x * x * x * x; }
 template <class T> inline T pow3(T x) { return x * x * x; }
@@ -700,6 +717,20 @@ inline bool fragment_from_ray(const Uniforms<T>& u, const Variant& var, vec3<T> 
     *out_albedo = {T(0), T(0), T(0)};
     *out_alpha = T(0);
     return true;
+}
+
+// MODE_FAR: is this pixel covered by the node's proxy BoxMesh (edge `clip_box_size`, centred on the node) and does the
+// cube's front face pass the depth test?  (engine rasteriser behaviour, restated; 0 = fullscreen quad)
+template <class T>
+inline bool far_box_covers(const Uniforms<T>& u, const mat4<T>& inv_view_matrix, T clip_box_size, vec3<T> ray_origin,
+                           vec3<T> ray_dir, T linear_depth) {
+    mat4<T> view_to_model_matrix = mul(u.u_world_to_model_matrix, inv_view_matrix);
+    vec4<T> o4 = mul(view_to_model_matrix, vec4<T>{ray_origin.x, ray_origin.y, ray_origin.z, T(1)});
+    vec4<T> d4 = mul(view_to_model_matrix, vec4<T>{ray_dir.x, ray_dir.y, ray_dir.z, T(0)});
+    T bs = clip_box_size * T(0.5);
+    vec2<T> rb = ray_box_intersection<T>({o4.x, o4.y, o4.z}, {d4.x, d4.y, d4.z}, {bs, bs, bs});
+    if (rb.x == T(-1) && rb.y == T(-1)) return false;
+    return rb.x > T(0) && rb.x < linear_depth;
 }
 
 // :69-104 — only the two varyings matter to a raymarcher

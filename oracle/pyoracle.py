@@ -174,6 +174,12 @@ def ray_sphere(center, radius, origin, direction, dtype=np.float32):
     return float(out[0]), float(out[1])
 
 
+def ray_box(ro, rd, box):
+    out = (C.c_float * 2)()
+    lib().oracle_ray_box_f32(_f3(ro), _f3(rd), _f3(box), out)
+    return float(out[0]), float(out[1])
+
+
 def atmosphere_density(params, height: float) -> float:
     return float(lib().oracle_atmosphere_density_f32(C.byref(params), C.c_float(height)))
 

@@ -286,6 +286,38 @@ def test_full_size_properties(cuda_ctx_factory):
     Hh.assert_rgba_close(f.reshape(-1, 4)[sel], ref, what="1080p sample")
 
 
+def test_far_mode_proxy_cube_coverage(cuda_ctx_factory):
+    """MODE_FAR (planet_atmosphere.gd:302-321): only pixels inside the proxy BoxMesh are shaded. Its half edge
+    0.9625*(R+H+near) is smaller than the atmosphere radius, so very distant face-on views lose a sliver of the limb
+    (a quirk of the reference's 1.75 ~ sqrt(3) margin) — replicated."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 256, 144
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds"])
+    # the cube's perspective silhouette only falls inside the atmosphere's for d > ~26 (R+H): a far, narrow view
+    cam = scenes.make_camera((0.0, 0.0, 6000.0), (0.0, 0.0, -1.0), aspect=w / h, near=1.0, far=20000.0, fovy_deg=2.4)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    out = {}
+    for name, size in (("near", 0.0), ("far", 1.75 * (100.0 + 8.0 + 0.1) * 1.1)):
+        cam.clip_box_size = size
+        rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+        disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+        ctx.render_frame(cam, d_depth, w, h, rgba, disc)
+        torch.cuda.synchronize()
+        ref, rdisc = O.render_frame(p, O.variant(8, 32, abi.LIGHT_CHEAP), cam, tex, depth, w, h, threads=0)
+        assert np.array_equal(disc.cpu().numpy(), rdisc)
+        Hh.assert_rgba_close(rgba.cpu().numpy(), ref, what=name)
+        out[name] = (rgba.cpu().numpy(), rdisc)
+    near_d, far_d = out["near"][1], out["far"][1]
+    assert np.all(far_d[near_d == 1] == 1)                      # the cube never adds pixels
+    lost = int(((far_d == 1) & (near_d == 0)).sum())
+    assert 0 < lost < 0.2 * (near_d == 0).sum()                 # ... and clips a thin sliver of the limb
+    keep = far_d == 0
+    assert np.array_equal(out["far"][0][keep], out["near"][0][keep])   # covered pixels are shaded identically
+
+
 def test_errors(cuda_ctx_factory):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     ctx = cuda_ctx_factory()

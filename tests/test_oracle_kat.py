@@ -28,6 +28,19 @@ def test_k1_ray_sphere():
     assert O.ray_sphere((0, 0, -5), 1.0, (0, 0, 0), (0, 0, -1), dtype=np.float64) == (4.0, 6.0)
 
 
+# include/util.gdshaderinc:5-17 (used for the MODE_FAR proxy-cube coverage)
+def test_ray_box_intersection():
+    assert O.ray_box((0, 0, -5), (0, 0, 1), (1, 1, 1)) == (4.0, 6.0)
+    assert O.ray_box((0, 0, 0), (0, 0, 1), (1, 2, 3)) == (-3.0, 3.0)            # origin inside
+    assert O.ray_box((0, 5, -5), (1e-3, 1e-3, 1), (1, 1, 1)) == (-1.0, -1.0)    # miss sentinel vec2(-1.0)
+    assert O.ray_box((0, 0, 5), (0, 0, 1), (1, 1, 1)) == (-1.0, -1.0)           # box behind the ray
+    # known flaw of the routine, kept: an exactly axis-parallel ray OUTSIDE a slab gives -inf/NaN bounds; GPU min/max
+    # ignore the NaN, so the slab is skipped and a hit is reported (measure-zero set of rays)
+    assert O.ray_box((0, 5, -5), (0, 0, 1), (1, 1, 1)) == (4.0, 6.0)
+    tn, tf = O.ray_box((-3, -3, -3), (1, 1, 1), (1, 1, 1))                       # un-normalised direction: t in its units
+    assert (tn, tf) == (2.0, 4.0)
+
+
 # K2 — include/atmosphere_common.gdshaderinc:12-24
 def test_k2_density():
     p = abi.default_params()

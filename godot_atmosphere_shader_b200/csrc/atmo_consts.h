@@ -91,6 +91,15 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
         c.shell_d2_lo = lo * lo;
         c.shell_d2_hi = hi * hi;
     }
+    {
+        // Largest value `shape` (cloud_funcs:48-59) can take for any texel in [0,1], in the shader's own arithmetic:
+        // mix(0.5, tex, factor) is monotone in tex, the optional invert flips it.
+        const float f = c.shape_factor;
+        const float s0 = 0.5f * (1.0f - f) + 0.0f * f, s1 = 0.5f * (1.0f - f) + 1.0f * f;
+        const float lo = s0 < s1 ? s0 : s1, hi = s0 < s1 ? s1 : s0;
+        const float shape_hi = c.shape_invert ? 1.0f - lo : hi;
+        c.shape_hi_m01 = shape_hi - 0.2f * 0.5f;
+    }
     c.cube_cells = t.cube_cells;
     c.cube_res = t.cube_res;
     c.shape_cells = t.shape_cells;

@@ -208,15 +208,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def load_traffic(a):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this workload."""
+def load_ncu_facts(a):
+    """Per-launch facts of the dominant kernel from the committed `ncu --set full` capture of this workload
+    (profiles/roofline_traffic.json): DRAM bytes (read+write) and executed warp instructions. {} if none."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         d = json.load(open(path))
-        key = f"{a.width}x{a.height}x{a.scatter_steps}_c{a.cloud_steps}_l{a.light}"
-        return d.get(key)
+        key = f"{a.width}x{a.height}x{a.scatter_steps}_c{a.cloud_steps}_l{a.light}_cam{a.camera}"
+        return d.get(key, {})
     except Exception:
-        return None
+        return {}
 
 
 def run_ours(a, rank, world, local_rank):
@@ -328,7 +329,17 @@ def run_ours(a, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = load_peaks()
+    facts = load_ncu_facts(a)
     achieved = ALGO_BYTES_PER_RAY * n_rays / (ms_per_step * 1e-3) / 1e9
+    # second roofline: the resource that actually binds this kernel is the warp-instruction issue rate
+    # (1 instr/clk/SMSP). Peak = 148 SMs x 4 SMSPs x SM clock under load.
+    issue = None
+    if facts.get("warp_instructions") and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        ipeak = sms * 4 * clocks["sm_mhz"] * 1e6
+        iach = facts["warp_instructions"] / (ms_per_step * 1e-3)
+        issue = {"bound": "issue", "achieved": iach / 1e9, "peak": ipeak / 1e9, "unit": "G warp-instr/s", "frac": iach / ipeak,
+                 "warp_instructions_per_launch": facts["warp_instructions"], "source": facts.get("source")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -342,12 +353,14 @@ def run_ours(a, rank, world, local_rank):
                 "timer": "host perf_counter around the synchronous call", "matches_device_path": e2e_ok},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(a), "peak_source": peak_src,
+                     "traffic": facts.get("dram_bytes"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_RAY * n_rays,
                      "kernel": "render_rays_kernel<V2, no clouds>" if not a.light else "render_rays_kernel<V2, clouds>",
                      "note": "FP32-issue/MUFU bound at N=32 by construction (1.5 B/ray-step); see DESIGN.md"},
         "timed_wall_s": wall, "checksum": checksum,
     }
+    if issue:
+        line["roofline_issue"] = issue
     if gather:
         line["gather"] = gather
     if world == 1 and not a.no_cpu_baseline:

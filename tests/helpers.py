@@ -164,3 +164,47 @@ def random_rays(n, params, seed=0, inside_fraction=0.3):
     fr.sun_center_view[:] = tuple(np.float32(sun).tolist())
     fr.inv_view[:] = abi.IDENTITY16
     return od, dj, fr
+
+
+def random_scene(seed):
+    """A seeded random uniform block + frame: planet scale over 3 decades, rotated/translated node transform, random
+    cloud shell, blend, bias, invert, coverage rotation, sphere-depth blend. Returns (params, frame, rays...)."""
+    from godot_atmosphere_shader_b200 import scenes as sc
+    rng = np.random.default_rng(seed)
+    p = sc.demo_params()
+    R = float(10.0 ** rng.uniform(0.0, 3.0))
+    H = R * float(rng.uniform(0.03, 0.25))
+    p.planet_radius, p.atmosphere_height = R, H
+    p.density = float(rng.uniform(0.5, 6.0)) / H              # optical thickness of order 1
+    p.scattering_strength = float(rng.uniform(0.3, 3.0))
+    p.scattering_wavelengths[:] = tuple(float(x) for x in (rng.uniform(620, 750), rng.uniform(500, 570), rng.uniform(420, 480)))
+    p.atmosphere_modulate[:] = tuple(float(x) for x in rng.uniform(0.5, 1.0, 3))
+    p.atmosphere_ambient_color[:] = tuple(float(x) for x in rng.uniform(0.0, 0.05, 3))
+    p.sphere_depth_factor = float(rng.choice([0.0, 0.0, 0.3, 1.0]))
+    b = float(rng.uniform(0.05, 0.5))
+    p.cloud_bottom, p.cloud_top = b, b + float(rng.uniform(0.1, 0.45))
+    p.cloud_density_scale = float(rng.uniform(0.5, 8.0)) * 8.0 / H
+    p.cloud_blend = float(rng.uniform(0.0, 1.0))
+    p.cloud_shape_invert = float(rng.integers(0, 2))
+    p.cloud_coverage_bias = float(rng.uniform(-0.2, 0.3))
+    p.cloud_shape_factor = float(rng.uniform(0.0, 1.0))
+    p.cloud_shape_scale = float(rng.uniform(2.0, 12.0)) / R
+    a = float(rng.uniform(0, 6.28))
+    p.cloud_coverage_rotation[:] = (np.cos(a), np.sin(a), -np.sin(a), np.cos(a))
+    # node transform: random rotation + translation; camera looks at the planet from 1.05 .. 4 radii
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    Rm = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                   [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                   [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    node = np.eye(4); node[:3, :3] = Rm; node[:3, 3] = rng.normal(size=3) * R * 3
+    p.world_to_model[:] = sc.flat_colmajor(np.linalg.inv(node))
+    dist = (R + H) * float(rng.uniform(1.02, 4.0)) if rng.random() < 0.7 else R + H * float(rng.uniform(0.05, 0.95))
+    dirv = rng.normal(size=3); dirv /= np.linalg.norm(dirv)
+    eye = node[:3, 3] + dirv * dist
+    side = np.cross(dirv, rng.normal(size=3)); side /= np.linalg.norm(side)
+    fwd = -dirv + side * float(rng.uniform(0.0, 0.6))
+    up = np.cross(fwd, side)
+    cam = sc.make_camera(eye, fwd, up=up, fovy_deg=float(rng.uniform(30, 90)), aspect=1.5, near=0.05 * H, far=50 * R, model=node)
+    p.sun_position[:] = tuple(float(v) for v in (node[:3, 3] + rng.normal(size=3) * 40 * R))
+    return p, cam

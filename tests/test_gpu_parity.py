@@ -318,6 +318,27 @@ def test_far_mode_proxy_cube_coverage(cuda_ctx_factory):
     assert np.array_equal(out["far"][0][keep], out["near"][0][keep])   # covered pixels are shaded identically
 
 
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("variant", ["no_clouds", "clouds_high", "clouds_high_rm"])
+def test_random_scenes_parity(cuda_ctx_factory, seed, variant):
+    """Random uniform blocks (planet scale over 3 decades, rotated + translated node, random cloud settings)."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    p, cam = Hh.random_scene(seed)
+    tex = _setup(ctx, p, VARIANTS[variant])
+    w, h = (72, 48) if VARIANTS[variant][3] == abi.LIGHT_RAYMARCHED else (144, 96)
+    depth = scenes.synth_depth(cam, p, w, h, planet_center=np.array(cam.model[:]).reshape(4, 4).T[:3, 3])
+    d_rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    d_disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, torch.from_numpy(depth).cuda(), w, h, d_rgba, d_disc)
+    torch.cuda.synchronize()
+    m, ns, nc, lm = VARIANTS[variant]
+    ref, rdisc = O.render_frame(p, O.variant(ns, nc, lm, m), cam, tex, depth, w, h, threads=0)
+    assert (rdisc == 0).mean() > 0.1, "scene does not look at the planet"
+    assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+    Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"random scene {seed}/{variant}")
+
+
 def test_errors(cuda_ctx_factory):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     ctx = cuda_ctx_factory()

@@ -12,7 +12,7 @@ from . import abi
 from .abi import B200AtmoCamera, B200AtmoFrame, B200AtmoParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200atmo.so")
+LIB_PATH = os.environ.get("B200ATMO_LIB", os.path.join(_HERE, "libb200atmo.so"))  # override: kernel-tuning builds only
 
 _lib = None
 

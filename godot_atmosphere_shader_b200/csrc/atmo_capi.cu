@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -506,20 +507,44 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     if ((rc = ensure(ctx, &ctx->d_stage_in0, &ctx->cap_in0, npx * sizeof(float))) != B200ATMO_OK) return rc;
     if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, npx * 4 * sizeof(float))) != B200ATMO_OK) return rc;
     if (h_discard && (rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_stage_disc), &ctx->cap_disc, npx)) != B200ATMO_OK) return rc;
+    if ((rc = bake_if_stale(ctx, ctx->streams[0])) != B200ATMO_OK) return rc;
     float* d_depth = static_cast<float*>(ctx->d_stage_in0);
     float* d_rgba = static_cast<float*>(ctx->d_stage_out);
-    // row bands, double-buffered over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band)
-    const int bands = h >= 64 ? 8 : 1;
-    for (int k = 0; k < bands; ++k) {
-        const int r0 = int((long long)h * k / bands), r1 = int((long long)h * (k + 1) / bands);
-        if (r0 == r1) continue;
+    DevConsts c;
+    if ((rc = frame_consts(ctx, cam, w, h, 0, h, c)) != B200ATMO_OK) return rc;
+    RayIO io{};
+    io.depth = d_depth;
+    io.rgba = d_rgba;
+    io.discard = h_discard ? ctx->d_stage_disc : nullptr;
+    io.n = npx;
+    // Row bands, alternating over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band). The D2H of 16 B/px
+    // is the PCIe-bound leg (4x the H2D), so the first band is small (the D2H engine starts early) and bands grow by
+    // ~1.5x: each band's upload + kernel hides behind the previous band's download. Few bands: the host issues
+    // ~3 API calls per band at ~5 us each.
+    int bands = h >= 256 ? 4 : 1;   // measured on B200: 3-5 bands are equivalent (0.72-0.75 ms at 1080p, PCIe floor 0.61 ms)
+    if (const char* e = std::getenv("B200ATMO_E2E_BANDS")) {  // experiment knob
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= h) bands = v;
+    }
+    const double r = 1.5;
+    double total = 0.0, acc = 0.0, pw = 1.0;
+    for (int k = 0; k < bands; ++k, pw *= r) total += pw;
+    pw = 1.0;
+    int r0 = 0;
+    for (int k = 0; k < bands; ++k, pw *= r) {
+        acc += pw;
+        const int r1 = (k == bands - 1) ? h : int(double(h) * acc / total);
+        if (r1 <= r0) continue;
         cudaStream_t s = ctx->streams[k & 1];
         const size_t off = size_t(r0) * w, cnt = size_t(r1 - r0) * w;
         CU_TRY(ctx, cudaMemcpyAsync(d_depth + off, h_depth + off, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
-        rc = b200atmo_render_frame(ctx, cam, d_depth, w, h, r0, r1, d_rgba, h_discard ? ctx->d_stage_disc : nullptr, s);
-        if (rc != B200ATMO_OK) return rc;
+        c.row_begin = r0;
+        c.row_end = r1;
+        CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+        ctx->launches++;
         CU_TRY(ctx, cudaMemcpyAsync(h_rgba + 4 * off, d_rgba + 4 * off, cnt * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard + off, ctx->d_stage_disc + off, cnt, cudaMemcpyDeviceToHost, s));
+        r0 = r1;
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));

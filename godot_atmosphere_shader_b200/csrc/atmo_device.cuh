@@ -23,6 +23,10 @@
 
 #include "atmo_internal.h"
 
+// tuning knobs (defaults chosen by profiles/tune_scatter.sh on B200)
+#ifndef B200ATMO_SCATTER_UNROLL
+#define B200ATMO_SCATTER_UNROLL 8
+#endif
 #define B200_PRAGMA(x) _Pragma(#x)
 #ifdef __CUDACC__
 #define B200_DEV __device__ __forceinline__
@@ -274,7 +278,7 @@ B200_DEV float4 scatter_v2(const DevConsts& c, f3 o, f3 d, float t_begin, float 
     const float4* cells = pin_reg(c.lut_cells);
     float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, view_od = 0.0f;
 
-B200_UNROLL(4)
+B200_UNROLL(B200ATMO_SCATTER_UNROLL)
     for (int i = 0; i < steps; ++i) {
         const f3 rel = pos - C;                                             // exact: carries the shader's position rounding
         const float d2 = fmaf(rel.z, rel.z, fmaf(rel.y, rel.y, rel.x * rel.x));

@@ -191,11 +191,19 @@ cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], 
 // ------------------------------------------------------------------------------------------------
 // render kernels
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlock = 128;
+#ifndef B200ATMO_BLOCK
+#define B200ATMO_BLOCK 128
+#endif
+#ifdef B200ATMO_MIN_BLOCKS
+#define B200ATMO_BOUNDS __launch_bounds__(B200ATMO_BLOCK, B200ATMO_MIN_BLOCKS)
+#else
+#define B200ATMO_BOUNDS __launch_bounds__(B200ATMO_BLOCK)
+#endif
+constexpr int kBlock = B200ATMO_BLOCK;
 
 // Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
 template <int MODEL, int LIGHT>
-__global__ void __launch_bounds__(kBlock) render_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+__global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
     const size_t i = blockIdx.x * size_t(kBlock) + threadIdx.x;
     if (i >= io.n) return;
     const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);

@@ -3,7 +3,7 @@
 #   -fmad=false + -ffp-contract=off : see the numeric policy in atmo_device.cuh
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="${HERE}/../libb200atmo.so"
+OUT="${B200ATMO_OUT:-${HERE}/../libb200atmo.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false
        -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall -Xptxas -v)

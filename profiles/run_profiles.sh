@@ -17,9 +17,12 @@ timeout 300 python bench.py --scatter-steps 8 --cloud-steps 64 --light 1 --camer
 timeout 600 python bench.py --width 3840 --height 2160 --scatter-steps 8 --cloud-steps 128 --light 2 --camera A --steps 10 --warmup 3 --e2e-steps 3 --no-cpu-baseline > gpurun_out/bench_cfg4_camA.json 2> gpurun_out/bench_cfg4.err
 # ncu: launch list of the default bench command, then full captures of the dominant kernels
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_cfg2.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_l.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 3 -c 1 -f -o gpurun_out/prof_cfg2_scatter32 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_a.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 3 -c 1 -f -o gpurun_out/prof_cfg3_clouds64_camA python bench.py --scatter-steps 8 --cloud-steps 64 --light 1 --camera A --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_b.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 2 -c 1 -f -o gpurun_out/prof_cfg4_rm128_camA python bench.py --width 1920 --height 1080 --scatter-steps 8 --cloud-steps 128 --light 2 --camera A --steps 2 --warmup 2 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_c.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 3 -c 1 -f -o gpurun_out/prof_1920x1080x32_c0_l0_camB python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_a.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 3 -c 1 -f -o gpurun_out/prof_1920x1080x8_c64_l1_camA python bench.py --scatter-steps 8 --cloud-steps 64 --light 1 --camera A --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_b.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 2 -c 1 -f -o gpurun_out/prof_1920x1080x8_c128_l2_camA python bench.py --width 1920 --height 1080 --scatter-steps 8 --cloud-steps 128 --light 2 --camera A --steps 2 --warmup 2 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_c.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_rays -s 3 -c 1 -f -o gpurun_out/prof_1920x1080x8_c0_l0_camB python bench.py --scatter-steps 8 --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_d.log 2>&1
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference_cfg2.json 2> gpurun_out/bench_reference.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --scatter-steps 8 --cloud-steps 64 --light 1 --camera A > gpurun_out/bench_reference_cfg3_camA.json 2>> gpurun_out/bench_reference.err
 cat gpurun_out/pytest_gpu.log
 for f in gpurun_out/bench_*.json; do echo "== $f"; python - "$f" <<'PY'
 import json,sys
@@ -29,4 +32,4 @@ try:
 except Exception as e: print("ERR", e)
 PY
 done
-tail -3 gpurun_out/bench_*.err
+for f in gpurun_out/bench_*.err; do tail -n 2 "$f"; done

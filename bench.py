@@ -134,13 +134,44 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the scalar C++ oracle on all host threads
 # ------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """Threads the CPU arm should use: min(hardware threads, scheduler affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    info = {"hardware_threads": n}
+    try:
+        aff = len(os.sched_getaffinity(0))
+        info["affinity"] = aff
+        n = min(n, aff)
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    q = max(1, int(float(txt[0]) / float(txt[1]) + 0.5))
+                    info["cgroup_quota_cpus"] = q
+                    n = min(n, q)
+            else:
+                quota = int(txt[0])
+                if quota > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    q = max(1, int(quota / period + 0.5))
+                    info["cgroup_quota_cpus"] = q
+                    n = min(n, q)
+            break
+        except Exception:
+            continue
+    return n, info
+
+
 def cpu_frame_runner(a, budget_s_per_step):
     """Returns (run, info): run() renders one bounded sample with the oracle and returns (seconds, ray_steps)."""
     from oracle import pyoracle as O
     p, cam, depth, tex = build_scene(a)
     otex = O.Textures(lut=O.bake_lut(p), shape=tex.get("shape"), cube_faces=tex.get("cube"), blue_noise=tex["bn"])
     var = O.variant(a.scatter_steps, a.cloud_steps, a.light)
-    threads = O.hardware_threads()
+    threads, cpu_info = usable_cpus()
     w, h = a.width, a.height
     od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
 
@@ -162,7 +193,7 @@ def cpu_frame_runner(a, budget_s_per_step):
     rows = np.arange(0, h, stride)
     idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
     s_od, s_dj = np.ascontiguousarray(od[idx]), np.ascontiguousarray(dj[idx])
-    info = {"cores": threads, "kind": "port",
+    info = {"cores": threads, "host": cpu_info, "kind": "port",
             "sample": (f"full {w}x{h} frame" if stride == 1 else f"every {stride}th row of the {w}x{h} frame ({len(rows)} rows)")
                       + f", {a.scatter_steps} steps, scalar C++ oracle -O2 no-FMA, {threads} std::thread workers"}
     return (lambda: render(s_od, s_dj)), info

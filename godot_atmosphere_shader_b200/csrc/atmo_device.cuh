@@ -30,6 +30,7 @@
 #define B200_PRAGMA(x) _Pragma(#x)
 #ifdef __CUDACC__
 #define B200_DEV __device__ __forceinline__
+#define B200_DEV_RARE __device__ __noinline__
 #define B200_UNROLL(n) B200_PRAGMA(unroll n)
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #else
@@ -38,6 +39,7 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #include <cmath>
 #include <cstring>
 #define B200_DEV static inline
+#define B200_DEV_RARE static inline
 struct float4 {
     float x, y, z, w;
 };
@@ -253,6 +255,33 @@ B200_DEV unsigned pin_reg(unsigned v) { return v; }
 B200_DEV const float4* pin_reg(const float4* v) { return v; }
 #endif
 
+// Rare path of scatter_v2: the literal alpha recurrence of funcs_v2:78-79 with a correctly rounded exp.
+// render_clouds' blend_colors (util:61-69) is DISCONTINUOUS at total alpha == 0 (it returns vec4(0)), so for rays that
+// barely touch the atmosphere with jitter == 0 it matters whether alpha is exactly 0: the shader's per-step
+// (1 - exp(-x)) terms all vanish for x <= 2^-25, while 1 - exp(-sum x) may not. Only rays with |view_od| < 2e-5 come
+// here (a thin rim of the limb). All ld_step share one sign, so each |x| <= |view_od| < 2e-5 and exp(-x) rounds like
+// 1 - x + x^2/2 (next term 1e-15): no fp64, no libm.
+B200_DEV_RARE float scatter_alpha_recurrence(const DevConsts& c, f3 o, f3 d, float t_begin, float step_len, int steps) {
+    const f3 C = ld3(c.C);
+    f3 pos = o + d * t_begin;
+    const f3 dstep = d * step_len;
+    const float ld_scale = c.rho2 * step_len;
+    const float neg_inv_H = -c.inv_H;
+    float alpha = 0.0f;
+    for (int i = 0; i < steps; ++i) {
+        const f3 rel = pos - C;
+        const float d2 = fmaf(rel.z, rel.z, fmaf(rel.y, rel.y, rel.x * rel.x));
+        float inv;
+        const float dist = sqrt_refined(d2, inv);
+        const float y = __saturatef(fmaf(dist - c.R, neg_inv_H, 1.0f));
+        const float ld_step = (y * y) * (y * ld_scale);
+        const float vt = 1.0f + fmaf(ld_step, 0.5f * ld_step, -ld_step);   // exp(-x) for tiny x, one final rounding  :78
+        alpha = alpha + (1.0f - vt) * (1.0f - alpha);    // :79
+        pos = pos + dstep;
+    }
+    return alpha;
+}
+
 // ------------------------------------------------------------------------------------------------
 // include/atmosphere_funcs_v2.gdshaderinc:32-101 — N-step in-scatter march against the baked LUT
 //
@@ -309,6 +338,7 @@ B200_UNROLL(B200ATMO_SCATTER_UNROLL)
     }
     // alpha: the recurrence a += (1-vt)(1-a), vt = exp(-ld*step) telescopes to 1 - exp(-view_od)  (:78-79)
     float alpha = 1.0f - ex2_approx(view_od * -1.4426950408889634f);
+    if (fabsf(view_od) < 2e-5f) alpha = scatter_alpha_recurrence(c, o, d, t_begin, step_len, steps);  // exact-zero cases
     const float r = clampf(fmaf(L0, c.coef[0], c.ambient[0]), 0.0f, 1.0f) * c.modulate[0];  // :91, :98
     const float g = clampf(fmaf(L1, c.coef[1], c.ambient[1]), 0.0f, 1.0f) * c.modulate[1];
     const float b = clampf(fmaf(L2, c.coef[2], c.ambient[2]), 0.0f, 1.0f) * c.modulate[2];

@@ -339,6 +339,86 @@ def test_random_scenes_parity(cuda_ctx_factory, seed, variant):
     Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"random scene {seed}/{variant}")
 
 
+@pytest.mark.parametrize("wh", [(1, 1), (3, 5), (17, 9), (130, 7)])
+def test_tiny_and_ragged_frames(cuda_ctx_factory, wh):
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = wh
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds"])
+    cam = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_rgba = torch.full((h, w, 4), -1.0, dtype=torch.float32, device="cuda")
+    d_disc = torch.full((h, w), 7, dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, torch.from_numpy(depth).cuda(), w, h, d_rgba, d_disc)
+    torch.cuda.synchronize()
+    ref, rdisc = O.render_frame(p, O.variant(8, 32, abi.LIGHT_CHEAP), cam, tex, depth, w, h)
+    assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+    Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"{w}x{h}")
+
+
+@pytest.mark.parametrize("steps", [(1, 1), (2, 3), (100, 1), (257, 300)])
+def test_extreme_step_counts(cuda_ctx_factory, steps):
+    """Step counts are runtime values: 1 step, counts that are not multiples of the unroll factor, very large counts."""
+    ctx = cuda_ctx_factory()
+    ns, nc = steps
+    p = scenes.demo_params()
+    variant = (abi.SCATTER_V2, ns, nc, abi.LIGHT_CHEAP)
+    tex = _setup(ctx, p, variant)
+    od, dj, fr = Hh.random_rays(1500, p, seed=ns * 1000 + nc)
+    got, gdisc = _render_rays_gpu(ctx, fr, od, dj)
+    ref, rdisc = O.render_rays(p, O.variant(ns, nc, abi.LIGHT_CHEAP), fr, tex, od, dj, threads=0)
+    assert np.array_equal(gdisc, rdisc)
+    Hh.assert_rgba_close(got, ref, what=f"steps {steps}")
+
+
+def test_non_finite_rays_do_not_fault(cuda_ctx_factory):
+    """NaN / Inf / zero-length inputs give NaN or garbage colours (as in the shader) but never an out-of-bounds access;
+    rays next to them are unaffected."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds_high_rm"])
+    od, dj, fr = Hh.random_rays(4096, p, seed=3)
+    bad = np.arange(0, 4096, 7)
+    od_b, dj_b = od.copy(), dj.copy()
+    od_b[bad[0::4], 0] = np.nan
+    dj_b[bad[1::4], :3] = 0.0
+    od_b[bad[2::4], 3] = np.inf
+    dj_b[bad[3::4], 1] = np.inf
+    # a ray through the planet centre with a sample exactly AT the centre: normalize(0) -> NaN in the shader
+    C = np.array(fr.planet_center_view[:], dtype=np.float32)
+    od_b[1] = (C[0], C[1], C[2] + 64.0, 1e4)
+    dj_b[1] = (0.0, 0.0, -1.0, 0.5)
+    got, gdisc = _render_rays_gpu(ctx, fr, od_b, dj_b)
+    torch.cuda.synchronize()
+    good = np.ones(4096, bool)
+    good[bad] = False
+    good[1] = False
+    ref, rdisc = O.render_rays(p, O.variant(8, 64, abi.LIGHT_RAYMARCHED), fr, tex, od[good], dj[good], threads=0)
+    assert np.array_equal(gdisc[good], rdisc)
+    Hh.assert_rgba_close(got[good], ref, what="finite neighbours")
+
+
+def test_camera_below_ground_and_inside_clouds(cuda_ctx_factory):
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 128, 72
+    p = scenes.demo_params()
+    tex = _setup(ctx, p, VARIANTS["clouds_high"])
+    # (an eye AT the planet centre makes the first sample normalize(0) = NaN in the shader: not a test case)
+    for eye in ((0.0, 99.0, 0.0), (0.0, 103.0, 0.0), (0.0, 107.9, 0.0), (0.0, 30.0, 0.0)):
+        cam = scenes.make_camera(eye, (0.3, 0.4, -1.0), aspect=w / h)
+        depth = np.zeros((h, w), np.float32)  # nothing opaque: the clear value
+        d_rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+        d_disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+        ctx.render_frame(cam, torch.from_numpy(depth).cuda(), w, h, d_rgba, d_disc)
+        torch.cuda.synchronize()
+        ref, rdisc = O.render_frame(p, O.variant(8, 64, abi.LIGHT_CHEAP), cam, tex, depth, w, h, threads=0)
+        assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+        Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"eye {eye}")
+
+
 def test_errors(cuda_ctx_factory):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     ctx = cuda_ctx_factory()

@@ -325,6 +325,15 @@ def run_ours(a, rank, world, local_rank):
     ms_per_step = ms_total / a.steps
     value = world * ray_steps / (ms_per_step * 1e-3)
 
+    # the frame API on device buffers (depth in, rays generated on the fly: 20 B/pixel instead of 48 B/ray)
+    d_rgba2 = torch.empty_like(d_rgba)
+    fms, _ = timed_loop(lambda: ctx.render_frame(cam, d_depth, w, h, d_rgba2, None, stream=stream), max(20, a.steps // 4), 3)
+    tf = torch.tensor([fms / max(20, a.steps // 4)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    frame_ms = float(tf.item())
+    frame_ok = bool(torch.equal(d_rgba2, d_rgba))
+
     # optional: compute + NCCL all-gather of the RGBA tiles (BASELINE config[4]); not part of `value`
     gather = None
     if world > 1:
@@ -383,6 +392,8 @@ def run_ours(a, rank, world, local_rank):
                 "api": "b200atmo_render_frame_host (pinned host depth in, RGBA out, 8 row bands over 2 streams)",
                 "timer": "host perf_counter around the synchronous call", "matches_device_path": e2e_ok},
         "gpu_launches": launches,
+        "frame_api": {"ms_per_step": frame_ms, "value": world * ray_steps / (frame_ms * 1e-3), "unit": UNIT,
+                      "api": "b200atmo_render_frame (device depth in, 4 B + 16 B per pixel)", "bit_identical_to_ray_api": frame_ok},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": facts.get("dram_bytes"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_RAY * n_rays,

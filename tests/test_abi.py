@@ -60,3 +60,17 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "hostsim" not in text.replace(
                     "tests/hostsim", ""), f"{f} references test infrastructure"
+
+
+@pytest.mark.gpu
+def test_c_client_example_builds_and_runs(tmp_path):
+    """examples/minimal.c: a plain C program against include/b200atmo.h (what a GDExtension would link)."""
+    import subprocess
+    exe = str(tmp_path / "minimal")
+    lib_dir = os.path.join(ROOT, "godot_atmosphere_shader_b200")
+    subprocess.check_call(["gcc", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "minimal.c"),
+                           "-L" + lib_dir, "-lb200atmo", "-Wl,-rpath," + lib_dir, "-lm", "-o", exe])
+    out = subprocess.check_output([exe], text=True)
+    vals = [float(x) for x in out.split("=")[1].split(";")[0].split()]
+    assert len(vals) == 4 and all(0.0 <= v <= 1.0 for v in vals) and vals[3] > 0.1   # looking at the planet: alpha well above 0
+    assert "kernels launched" in out

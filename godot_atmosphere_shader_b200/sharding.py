@@ -55,3 +55,30 @@ def render_frame_sharded(ctx, cam, d_depth, width: int, height: int, rank: int, 
         full = gather_bands(d_rgba_full[b:e], height, width, rank, world)
         d_rgba_full.copy_(full.reshape(d_rgba_full.shape))
     return d_rgba_full
+
+
+def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int, d_tiles, rank: int, world: int, chunks: int = 4,
+                                      stream=None):
+    """Weak-scaling delivery (BASELINE config[4] shape): every rank renders its OWN width x height tile and all ranks
+    end up with all tiles in `d_tiles` ([world, height, width, 4] on this rank's GPU).
+
+    The tile is rendered in `chunks` row chunks on the current stream; as soon as a chunk is launched its all-gather is
+    issued asynchronously (torch.distributed runs NCCL on its own stream and makes it wait for the work already
+    queued on the current stream), so the NVLink transfer of chunk k overlaps the rendering of chunk k+1.
+    Returns after all gathers are complete on the current stream.
+    """
+    import torch.distributed as dist
+
+    mine = d_tiles[rank]
+    works = []
+    for k in range(chunks):
+        r0, r1 = (height * k) // chunks, (height * (k + 1)) // chunks
+        if r1 <= r0:
+            continue
+        ctx.render_frame(cam, d_depth, width, height, mine, None, row_begin=r0, row_end=r1, stream=stream)
+        if world > 1:
+            outs = [d_tiles[r, r0:r1] for r in range(world)]
+            works.append(dist.all_gather(outs, mine[r0:r1], async_op=True))
+    for wk in works:
+        wk.wait()
+    return d_tiles

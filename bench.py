@@ -223,7 +223,7 @@ def run_reference(a, rank, world):
         "gpu_launches": 0,
         "note": "the reference ships no CPU implementation (GDShader only); this arm is the scalar C++ oracle port",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -425,12 +425,35 @@ def run_ours(a, rank, world, local_rank):
         ts = [run() for _ in range(3)]
         best = min(ts, key=lambda x: x[0])
         line["cpu_baseline"] = dict(info, value=best[1] / best[0], unit=UNIT, ms_per_step=best[0] * 1e3)
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything any library prints to fd 1 (NCCL's "NCCL version ..." banner goes to stdout) is routed to stderr; the
+    single JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        n = os.write(fd, data)
+        data = data[n:]
 
 
 def main():
     a = parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -57,28 +57,27 @@ def render_frame_sharded(ctx, cam, d_depth, width: int, height: int, rank: int, 
     return d_rgba_full
 
 
-def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int, d_tiles, rank: int, world: int, chunks: int = 4,
-                                      stream=None):
-    """Weak-scaling delivery (BASELINE config[4] shape): every rank renders its OWN width x height tile and all ranks
-    end up with all tiles in `d_tiles` ([world, height, width, 4] on this rank's GPU).
+def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int, d_mine, d_chunks, rank: int, world: int,
+                                      chunks: int = 4, stream=None):
+    """Weak-scaling delivery (BASELINE config[4] shape): every rank renders its OWN width x height tile (`d_mine`,
+    [height, width, 4]) and all ranks receive all tiles.
 
-    The tile is rendered in `chunks` row chunks on the current stream; as soon as a chunk is launched its all-gather is
-    issued asynchronously (torch.distributed runs NCCL on its own stream and makes it wait for the work already
-    queued on the current stream), so the NVLink transfer of chunk k overlaps the rendering of chunk k+1.
-    Returns after all gathers are complete on the current stream.
+    The tile is rendered in `chunks` equal row chunks on the current stream; right after a chunk is launched its
+    all-gather is issued asynchronously (torch.distributed runs NCCL on its own stream and makes it wait for the work
+    already queued on the current stream), so the NVLink transfer of chunk k overlaps the rendering of chunk k+1.
+    `d_chunks` is the receive buffer in CHUNK-MAJOR layout [chunks, world, height/chunks, width, 4]: each collective
+    writes one contiguous slab (no staging copies); tile r, rows of chunk k = d_chunks[k, r]. height % chunks == 0.
     """
     import torch.distributed as dist
 
-    mine = d_tiles[rank]
+    assert height % chunks == 0, "chunked gather needs equal row chunks"
+    rows = height // chunks
     works = []
     for k in range(chunks):
-        r0, r1 = (height * k) // chunks, (height * (k + 1)) // chunks
-        if r1 <= r0:
-            continue
-        ctx.render_frame(cam, d_depth, width, height, mine, None, row_begin=r0, row_end=r1, stream=stream)
+        r0, r1 = k * rows, (k + 1) * rows
+        ctx.render_frame(cam, d_depth, width, height, d_mine, None, row_begin=r0, row_end=r1, stream=stream)
         if world > 1:
-            outs = [d_tiles[r, r0:r1] for r in range(world)]
-            works.append(dist.all_gather(outs, mine[r0:r1], async_op=True))
+            works.append(dist.all_gather_into_tensor(d_chunks[k].view(world * rows, width, 4), d_mine[r0:r1], async_op=True))
     for wk in works:
         wk.wait()
-    return d_tiles
+    return d_chunks

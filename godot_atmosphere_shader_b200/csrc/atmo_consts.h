@@ -84,12 +84,6 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
         c.march_hmin = c.cloud_bottom_h;                                         // :191
         c.march_hmax = c.cloud_top_h * 1.05f;                                    // :192
         c.light_reach = (c.cloud_top_h - c.cloud_bottom_h) * 0.15f;              // :108
-        // pre-test bounds: a sample with |p|^2 outside [lo, hi] is certainly outside the shell (height_curve <= 0, density
-        // exactly 0); the 1e-5 relative margin is ~100x the rounding of the exact chain sqrt -> (len-bottom)/thickness ->
-        // 1-(2hr-1)^2, which still decides every sample inside the margin.
-        const float lo = c.cloud_bottom_h * (1.0f - 1e-5f), hi = c.cloud_top_h * (1.0f + 1e-5f);
-        c.shell_d2_lo = lo * lo;
-        c.shell_d2_hi = hi * hi;
     }
     {
         // Largest value `shape` (cloud_funcs:48-59) can take for any texel in [0,1], in the shader's own arithmetic:

@@ -417,9 +417,6 @@ B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
     return __saturatef(density);                                               // :64
 }
 
-// Conservative pre-test on |p|^2 (no sqrt): false => certainly outside the shell => density exactly 0 (see atmo_consts.h)
-B200_DEV bool cloud_in_shell_maybe(const DevConsts& c, float d2) { return d2 > c.shell_d2_lo && d2 < c.shell_d2_hi; }
-
 // get_light_raymarched (:104-151)
 B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0) {
     float step_len = c.light_reach * (1.0f / 6.0f);   // reach * inv_steps
@@ -428,14 +425,11 @@ B200_UNROLL(1)
     for (int i = 0; i < 6; ++i) {
         const float t = float(i) * step_len;
         const f3 p = mk3(pos0.x + t * sun.x, pos0.y + t * sun.y, pos0.z + t * sun.z);  // :129, exact
-        const float d2 = dot3(p, p);
-        if (cloud_in_shell_maybe(c, d2)) {
-            float inv;
-            const float len = sqrt_refined(d2, inv);
-            const float dens = cloud_density(c, p, cloud_height_ratio(c, len));
-            if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.density_scale) * -1.4426950408889634f);  // :138-142
-        }
-        step_len *= 1.2f;                                                                                       // :143
+        float inv;
+        const float len = sqrt_refined(dot3(p, p), inv);
+        const float dens = cloud_density(c, p, cloud_height_ratio(c, len));
+        if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.density_scale) * -1.4426950408889634f);  // :138-142
+        step_len *= 1.2f;                                                                                   // :143
     }
     const float alpha = 1.0f - transm;
     return mixf(1.0f, hr0 * 0.2f, alpha);              // :146-150
@@ -467,13 +461,10 @@ template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, 
     float total_light = 0.0f;
 B200_UNROLL(1)
     for (int i = 0; i < steps; ++i) {
-        const float d2 = dot3(pos, pos);
-        float inv = 0.0f, len = 0.0f, hr = 0.0f, dens01 = 0.0f;
-        if (cloud_in_shell_maybe(c, d2)) {
-            len = sqrt_refined(d2, inv);
-            hr = cloud_height_ratio(c, len);
-            dens01 = cloud_density(c, pos, hr);
-        }
+        float inv;
+        const float len = sqrt_refined(dot3(pos, pos), inv);
+        const float hr = cloud_height_ratio(c, len);
+        const float dens01 = cloud_density(c, pos, hr);
         if (dens01 > 0.0f) {  // density == 0 => transmittance 1, no light added, alpha unchanged: exact skip
             float light;      // get_light (:153-167)
             if (LIGHT == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched(c, pos, sun, hr);

@@ -49,7 +49,6 @@ struct DevConsts {
     float march_hmin, march_hmax;        // cloud_funcs:191-192
     float light_reach;                   // (top-bottom)*0.15, cloud_funcs:108
     float shape_hi_m01;                  // upper bound of (shape - 0.2*detail) over all texel values, see cloud_density
-    float shell_d2_lo, shell_d2_hi;      // conservative |p|^2 bounds of the cloud shell (pre-test only, see cloud_in_shell_maybe)
     const float4* cube_cells;            // [6][res+1][res+1] bilinear footprints of the seamless padded faces (u8/255 as fp32)
     int cube_res;
     const float4* shape_cells;           // [nz+1][ny+1][nx+1][2] trilinear footprints of the repeat-padded volume

@@ -22,7 +22,7 @@ EXPORTS = [
     "b200atmo_destroy", "b200atmo_last_error", "b200atmo_default_params", "b200atmo_set_params", "b200atmo_get_params",
     "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube", "b200atmo_generate_noise_cubemap",
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
-    "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_make_rays", "b200atmo_render_frame_host",
+    "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
     "b200atmo_launch_count",
 ]
 
@@ -65,6 +65,7 @@ def lib():
         L.b200atmo_render_rays.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, sz, vp, vp, vp]
         L.b200atmo_render_rays_host.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, sz, vp, vp]
         L.b200atmo_render_frame.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, vp, vp]
+        L.b200atmo_render_frame_composite.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, vp]
         L.b200atmo_make_rays.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, C.POINTER(B200AtmoFrame), vp]
         L.b200atmo_render_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp]
         L.b200atmo_launch_count.argtypes = [vp]
@@ -188,6 +189,11 @@ class AtmosphereContext:
     def render_frame(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, row_begin=0, row_end=None, stream=None):
         self._check(lib().b200atmo_render_frame(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
                                                 int(h if row_end is None else row_end), _dptr(rgba), _dptr(discard), stream))
+
+    def render_frame_composite(self, cam: B200AtmoCamera, depth, w, h, color_inout, row_begin=0, row_end=None, stream=None):
+        """Render and alpha-blend into the frame's colour buffer (float4 per pixel) like the ROP's blend_mix."""
+        self._check(lib().b200atmo_render_frame_composite(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
+                                                          int(h if row_end is None else row_end), _dptr(color_inout), stream))
 
     def make_rays(self, cam: B200AtmoCamera, depth, w, h, origin_depth, dir_jitter, stream=None) -> B200AtmoFrame:
         fr = B200AtmoFrame()

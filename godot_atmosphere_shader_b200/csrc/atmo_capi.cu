@@ -466,6 +466,26 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
     return B200ATMO_OK;
 }
 
+int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                    int row_begin, int row_end, float* d_color_inout, void* stream) {
+    if (!ctx || !cam || !d_depth || !d_color_inout)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_composite: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = bake_if_stale(ctx, s);
+    if (rc != B200ATMO_OK) return rc;
+    DevConsts c;
+    if ((rc = frame_consts(ctx, cam, w, h, row_begin, row_end, c)) != B200ATMO_OK) return rc;
+    if (row_begin == row_end) return B200ATMO_OK;
+    RayIO io{};
+    io.depth = d_depth;
+    io.color_inout = d_color_inout;
+    io.n = size_t(w) * h;
+    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
 int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, float* d_origin_depth,
                        float* d_dir_jitter, B200AtmoFrame* frame_out, void* stream) {
     if (!ctx || !cam || !d_depth || !d_origin_depth || !d_dir_jitter)

@@ -69,6 +69,7 @@ struct RayIO {
     const void* dir_jitter;    // float4[n]
     const float* depth;        // float[w*h]  frame in
     void* rgba;                // float4[...] out
+    void* color_inout;         // float4[w*h] frame colour buffer to blend into (frame kernel; then rgba may be null)
     uint8_t* discard;          // nullable
     void* out_origin_depth;    // make_rays only
     void* out_dir_jitter;

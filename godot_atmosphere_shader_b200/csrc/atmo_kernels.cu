@@ -230,7 +230,16 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
     bool disc = true;
     if (!(c.clip_box_half > 0.0f) || far_box_covers(c, o, d, linear_depth))  // MODE_FAR: outside the proxy cube = not rasterised
         disc = shade_ray<MODEL, LIGHT>(c, o, d, linear_depth, jitter, out);
-    __stcs(static_cast<float4*>(io.rgba) + i, out);
+    if (io.color_inout) {  // the ROP's blend_mix of an unshaded spatial shader, exact arithmetic; discard = no write
+        if (!disc) {
+            float4* dst = static_cast<float4*>(io.color_inout) + i;
+            const float4 bg = *dst;
+            const float ia = 1.0f - out.w;
+            *dst = make_float4(out.x * out.w + bg.x * ia, out.y * out.w + bg.y * ia, out.z * out.w + bg.z * ia, bg.w);
+        }
+    } else {
+        __stcs(static_cast<float4*>(io.rgba) + i, out);
+    }
     if (io.discard) io.discard[i] = disc ? 1 : 0;
 }
 

@@ -211,6 +211,12 @@ int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
 int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth,
                           int w, int h, int row_begin, int row_end,
                           float* d_rgba, uint8_t* d_discard, void* stream);
+/* Same as b200atmo_render_frame, but the result is alpha-blended straight into the frame's colour buffer, which is what
+ * the reference's `render_mode unshaded` + default blend_mix does in the ROP (planet_atmosphere_*.gdshader:2):
+ *   color.rgb = ALBEDO * ALPHA + color.rgb * (1 - ALPHA)   for every non-discarded pixel;  color.a is left untouched.
+ * d_color_inout: w*h float4 (linear HDR colour), rows [row_begin,row_end) are updated in place. */
+int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                    int row_begin, int row_end, float* d_color_inout, void* stream);
 /* Frame front-end only (main:101-103,128-142): depth buffer -> the SoA ray buffers of the ray-batch API and
  * the frame constants that go with them (frame_out may be NULL). */
 int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,

@@ -419,6 +419,35 @@ def test_camera_below_ground_and_inside_clouds(cuda_ctx_factory):
         Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"eye {eye}")
 
 
+def test_composite_equals_render_then_blend(cuda_ctx_factory):
+    """b200atmo_render_frame_composite == render_frame followed by blend_mix (src*a + dst*(1-a)), bit for bit;
+    discarded pixels and the destination alpha are untouched."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 320, 180
+    p = scenes.demo_params()
+    _setup(ctx, p, VARIANTS["clouds"])
+    cam = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, rgba, disc)
+    rng = np.random.default_rng(0)
+    bg = rng.uniform(0, 4, size=(h, w, 4)).astype(np.float32)        # an HDR frame
+    color = torch.from_numpy(bg.copy()).cuda()
+    ctx.render_frame_composite(cam, d_depth, w, h, color, row_begin=0, row_end=h // 2)
+    ctx.render_frame_composite(cam, d_depth, w, h, color, row_begin=h // 2, row_end=h)
+    torch.cuda.synchronize()
+    src, d = rgba.cpu().numpy(), disc.cpu().numpy()
+    a = src[..., 3:4]
+    want = bg.copy()
+    want[..., :3] = src[..., :3] * a + bg[..., :3] * (np.float32(1.0) - a)
+    want[d == 1] = bg[d == 1]
+    assert np.array_equal(color.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert (d == 1).any() and (d == 0).any()
+
+
 def test_errors(cuda_ctx_factory):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     ctx = cuda_ctx_factory()

@@ -288,7 +288,8 @@ int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps
     if (!ctx) return B200ATMO_E_INVALID;
     if (scatter_model != B200ATMO_SCATTER_V2 && scatter_model != B200ATMO_SCATTER_V1)
         return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: unknown scatter model");
-    if (scatter_steps < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: scatter_steps must be >= 1");
+    if (scatter_steps < 1 || scatter_steps > 65536 || cloud_steps > 65536)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: step counts must be in [1, 65536]");
     if (light_mode < B200ATMO_LIGHT_NONE || light_mode > B200ATMO_LIGHT_RAYMARCHED)
         return fail(ctx, B200ATMO_E_INVALID, "b200atmo_set_variant: unknown light mode");
     if (light_mode != B200ATMO_LIGHT_NONE && cloud_steps < 1)

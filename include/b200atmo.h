@@ -142,7 +142,7 @@ void b200atmo_default_params(B200AtmoParams* out);
 int b200atmo_set_params(b200atmo_ctx* ctx, const B200AtmoParams* p);
 int b200atmo_get_params(const b200atmo_ctx* ctx, B200AtmoParams* out);
 /* Replaces: custom_shader selection, i.e. the compile-time #defines of the entry shaders
- * (shaders/planet_atmosphere_*.gdshader:4-7). scatter_steps >= 1; cloud_steps >= 1 unless light_mode is NONE. */
+ * (shaders/planet_atmosphere_*.gdshader:4-7). 1 <= scatter_steps <= 65536; 1 <= cloud_steps <= 65536 unless light_mode is NONE. */
 int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps, int cloud_steps, int light_mode);
 
 /* ---- textures (host -> device; the context keeps its own device copy) -------------------------- */

@@ -448,11 +448,64 @@ def test_composite_equals_render_then_blend(cuda_ctx_factory):
     assert (d == 1).any() and (d == 0).any()
 
 
+def test_garbage_uniforms_never_fault(cuda_ctx_factory):
+    """Fuzz: extreme / zero / negative / NaN / Inf uniform blocks and matrices. The shader would output garbage; the
+    library must too — but without an illegal address or a hang, and the context must keep working afterwards."""
+    torch = _torch()
+    import ctypes as C
+    ctx = cuda_ctx_factory()
+    shape, cube, bn = Hh.demo_textures()
+    ctx.upload_shape3d(shape); ctx.upload_coverage_cube(cube); ctx.upload_blue_noise(bn)
+    w, h = 64, 36
+    rng = np.random.default_rng(1234)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, 1e-30, 1e30, -1e30, np.inf, -np.inf, np.nan, 3.4e38, 1e-45], np.float32)
+    base = scenes.demo_params()
+    nfloats = C.sizeof(abi.B200AtmoParams) // 4
+    cam0 = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam0, base, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    d_rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    for it in range(60):
+        raw = np.frombuffer(bytes(base), dtype=np.float32).copy()
+        k = rng.integers(1, 12)
+        idx = rng.choice(nfloats, size=k, replace=False)
+        raw[idx] = rng.choice(specials, size=k)
+        if it % 3 == 0:
+            raw[rng.choice(nfloats, size=4, replace=False)] = (rng.normal(size=4) * 10.0 ** rng.uniform(-6, 6, size=4)).astype(np.float32)
+        p = abi.B200AtmoParams.from_buffer_copy(raw.tobytes())
+        cam = scenes.camera_a(w, h)
+        if it % 4 == 1:
+            m = np.array(cam.inv_view[:], dtype=np.float32)
+            m[rng.integers(0, 16)] = rng.choice(specials)
+            cam.inv_view[:] = tuple(m.tolist())
+        if it % 5 == 2:
+            m = np.array(cam.inv_projection[:], dtype=np.float32)
+            m[rng.integers(0, 16)] = rng.choice(specials)
+            cam.inv_projection[:] = tuple(m.tolist())
+        cam.clip_box_size = float(rng.choice([0.0, 0.0, 208.0, np.nan, -5.0, np.inf]))
+        ctx.set_params(p)
+        ctx.set_variant(int(rng.integers(1, 20)), int(rng.integers(1, 40)), int(rng.integers(0, 3)), int(rng.integers(0, 2)))
+        ctx.render_frame(cam, d_depth, w, h, d_rgba, None)
+        torch.cuda.synchronize()  # an illegal address would surface here
+    # the context is still healthy: a clean render matches the oracle
+    tex = _setup(ctx, base, VARIANTS["clouds"])
+    d_disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    ctx.render_frame(cam0, d_depth, w, h, d_rgba, d_disc)
+    torch.cuda.synchronize()
+    ref, rdisc = O.render_frame(base, O.variant(8, 32, abi.LIGHT_CHEAP), cam0, tex, depth, w, h)
+    assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+    Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what="after fuzz")
+
+
 def test_errors(cuda_ctx_factory):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     ctx = cuda_ctx_factory()
     with pytest.raises(B200AtmoError):
         ctx.set_variant(0)
+    with pytest.raises(B200AtmoError):
+        ctx.set_variant(100000)
+    with pytest.raises(B200AtmoError):
+        ctx.set_variant(8, 100000, abi.LIGHT_CHEAP)
     with pytest.raises(B200AtmoError):
         ctx.set_variant(8, 0, abi.LIGHT_CHEAP)
     with pytest.raises(B200AtmoError):

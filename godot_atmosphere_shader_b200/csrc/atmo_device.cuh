@@ -299,13 +299,15 @@ B200_DEV float4 scatter_v2(const DevConsts& c, f3 o, f3 d, float t_begin, float 
     const float step_len = (t_end - t_begin) / float(steps);
     f3 pos = o + d * t_begin;   // pos0, :57-58 (exact)
     const f3 dstep = d * step_len;
-    const float ld_scale = c.rho2 * step_len;  // get_atmosphere_density()*u_density*step_len = y^3 * rho^2 * step_len
+    // local_density*step_len = y^3 * (rho^2 * step_len): the constant factor is applied once after the loop, the loop
+    // accumulates S = sum y^3 (view optical depth / ld_scale) and sum y^3 * T_c
+    const float ld_scale = c.rho2 * step_len;
     const float k0 = c.neg_coef_log2e[0], k1 = c.neg_coef_log2e[1], k2 = c.neg_coef_log2e[2];
     const float neg_inv_H = pin_reg(-c.inv_H);
     const float n256 = pin_reg(-256.0f);
     constexpr unsigned off_bias = 0u - unsigned(kMagicBits) * unsigned(kLutCells + 1);  // both magic biases, mod 2^32
     const float4* cells = pin_reg(c.lut_cells);
-    float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, view_od = 0.0f;
+    float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, S = 0.0f;
 
 B200_UNROLL(B200ATMO_SCATTER_UNROLL)
     for (int i = 0; i < steps; ++i) {
@@ -316,32 +318,34 @@ B200_UNROLL(B200ATMO_SCATTER_UNROLL)
         const float dist = sqrt_refined(d2, inv);                           // distance(pos, planet_center)
         // y = 1 - clamp((dist-R)/H, 0, 1) in one rounding (atmosphere_common:13-15); height_ratio (:17-18) = 1 - y
         const float y = __saturatef(fmaf(dist - c.R, neg_inv_H, 1.0f));
-        const float mu128 = sd * inv;                                       // 128 * dot(normalize(pos-C), sun_dir), :19-20
-        const float xm = mu128 + (kMagic + 128.0f);                         // integer part n_x in the low mantissa bits
-        const float ym = fmaf(y, n256, kMagic + 256.0f);
-        const float g = mu128 - (xm - (kMagic + 128.0f));                   // centred fractions in [-0.5, 0.5]
-        const float h = fmaf(y, n256, 256.0f - (ym - kMagic));
+        // 128*mu = sd*inv = 128 * dot(normalize(pos-C), sun_dir) (:19-20) is never materialised: one fma gives the cell
+        // column n_x = rn(128 mu + 128) in the low mantissa bits, a second one the centred fraction g = (128 mu + 128) - n_x
+        const float xm = fmaf(sd, inv, kMagic + 128.0f);
+        const float ym = fmaf(y, n256, kMagic + 256.0f);                    // cell row n_y = rn(256 - 256 y)
+        const float g = fmaf(sd, inv, (kMagic + 128.0f) - xm);              // centred fractions in [-0.5, 0.5]
+        const float h = fmaf(y, n256, (kMagic + 256.0f) - ym);              // (256 - 256 y) - n_y
         // row*257 + col; the unsigned min turns the garbage of a NaN coordinate (pos == planet centre) into an
         // in-range read instead of a fault
         unsigned off = unsigned(__float_as_int(ym)) * unsigned(kLutCells) + unsigned(__float_as_int(xm));
         off = min(off + off_bias, unsigned(kLutCells * kLutCells - 1));
         const float4 q = ldg4(cells + off);                                 // :28
         const float sun_od = fmaf(fmaf(q.w, g, q.z), h, fmaf(q.y, g, q.x));
-        const float ld_step = (y * y) * (y * ld_scale);                     // local_density * step_len, :64-65
-        view_od += ld_step;                                                 // :66
-        const float od = sun_od + view_od;
+        const float y3 = (y * y) * y;                                       // local_density*step_len / ld_scale, :64-65
+        S += y3;                                                            // :66
+        const float od = fmaf(S, ld_scale, sun_od);                         // sun_ray + view_ray optical depth
         const float T0 = ex2_approx(od * k0), T1 = ex2_approx(od * k1), T2 = ex2_approx(od * k2);  // :71-73
-        L0 = fmaf(ld_step, T0, L0);                                         // :75 (coefficient applied after the loop)
-        L1 = fmaf(ld_step, T1, L1);
-        L2 = fmaf(ld_step, T2, L2);
+        L0 = fmaf(y3, T0, L0);                                              // :75 (ld_scale and the coefficient are applied after the loop)
+        L1 = fmaf(y3, T1, L1);
+        L2 = fmaf(y3, T2, L2);
         pos = pos + dstep;                                                  // :81 (exact)
     }
+    const float view_od = S * ld_scale;
     // alpha: the recurrence a += (1-vt)(1-a), vt = exp(-ld*step) telescopes to 1 - exp(-view_od)  (:78-79)
     float alpha = 1.0f - ex2_approx(view_od * -1.4426950408889634f);
     if (fabsf(view_od) < 2e-5f) alpha = scatter_alpha_recurrence(c, o, d, t_begin, step_len, steps);  // exact-zero cases
-    const float r = clampf(fmaf(L0, c.coef[0], c.ambient[0]), 0.0f, 1.0f) * c.modulate[0];  // :91, :98
-    const float g = clampf(fmaf(L1, c.coef[1], c.ambient[1]), 0.0f, 1.0f) * c.modulate[1];
-    const float b = clampf(fmaf(L2, c.coef[2], c.ambient[2]), 0.0f, 1.0f) * c.modulate[2];
+    const float r = clampf(fmaf(L0 * ld_scale, c.coef[0], c.ambient[0]), 0.0f, 1.0f) * c.modulate[0];  // :91, :98
+    const float g = clampf(fmaf(L1 * ld_scale, c.coef[1], c.ambient[1]), 0.0f, 1.0f) * c.modulate[1];
+    const float b = clampf(fmaf(L2 * ld_scale, c.coef[2], c.ambient[2]), 0.0f, 1.0f) * c.modulate[2];
     alpha = clampf(fmaf(jitter, 0.02f, alpha), 0.0f, 0.99f);                                 // :96
     return make_float4(r, g, b, alpha);
 }

@@ -156,17 +156,6 @@ B200_DEV f2 ray_sphere(f3 center, float radius, f3 ray_origin, f3 ray_dir) {
 // ------------------------------------------------------------------------------------------------
 // texture fetches in the hot loops (textures are fp32 copies with a one-texel apron, see atmo_kernels.cu)
 // ------------------------------------------------------------------------------------------------
-// texture(u_optical_depth_texture, vec2(u, v)).r — funcs_v2:28; u,v in [0,1] (caller clamps)
-B200_DEV float sample_lut(const float* __restrict__ lut_pad, float u, float v) {
-    float fx, fy;
-    const int xi = floor_frac(u * float(kLut) - 0.5f, fx) + 1;  // padded index of the left texel, 0..256
-    const int yi = floor_frac(v * float(kLut) - 0.5f, fy) + 1;
-    const float* p = lut_pad + yi * kLutPad + xi;
-    const float t00 = __ldg(p), t10 = __ldg(p + 1);
-    const float t01 = __ldg(p + kLutPad), t11 = __ldg(p + kLutPad + 1);
-    return lerp_fma(lerp_fma(t00, t10, fx), lerp_fma(t01, t11, fx), fy);
-}
-
 // ---- cell layouts of the two noise textures ------------------------------------------------------
 // Built once at upload (atmo_kernels.cu) from the padded fp32 copies. A cell holds the texels of one
 // interpolation footprint with the x-differences precomputed, so a fetch is 1 (cube) / 2 (3D) 16-byte loads and the

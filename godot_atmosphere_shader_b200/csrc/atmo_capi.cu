@@ -22,13 +22,9 @@ struct b200atmo_ctx {
     float* d_lut = nullptr;       // [256][256]
     float* d_lut_pad = nullptr;   // [258][258]
     float4* d_lut_cells = nullptr; // [257][257] bilinear cells
-    uint8_t* d_cube_raw = nullptr;
     uint8_t* d_cube_pad_u8 = nullptr;
-    float* d_cube_pad = nullptr;
     float4* d_cube_cells = nullptr;
     int cube_res = 0;
-    uint8_t* d_shape_raw = nullptr;
-    float* d_shape_pad = nullptr;
     float4* d_shape_cells = nullptr;
     int nx = 0, ny = 0, nz = 0;
     uint8_t* d_blue = nullptr;
@@ -113,50 +109,55 @@ int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
     return B200ATMO_OK;
 }
 
-// installs a cube whose raw faces are either on the host (h_faces6) or already on the device (d_src)
+// device allocation that frees itself unless released (no leaks on the error paths of the upload functions)
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    template <class T> T* release() {
+        T* q = static_cast<T*>(p);
+        p = nullptr;
+        return q;
+    }
+};
+
+// installs a cube whose raw faces are either on the host (h_faces6) or already on the device (d_src); the raw faces and
+// the padded fp32 copy only live during the build, the context keeps the integer seamless layout (for
+// b200atmo_download_cube_padded) and the cells the kernels sample
 int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_t s, const uint8_t* d_src = nullptr) {
     const size_t raw = size_t(6) * res * res, pad = size_t(6) * (res + 2) * (res + 2);
-    uint8_t *d_raw = nullptr, *d_pad8 = nullptr;
-    float* d_pad = nullptr;
-    float4* d_cells = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d_raw, raw));
-    CU_TRY(ctx, cudaMalloc(&d_pad8, pad));
-    CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
-    CU_TRY(ctx, cudaMalloc(&d_cells, size_t(6) * (res + 1) * (res + 1) * sizeof(float4)));
-    CU_TRY(ctx, cudaMemcpyAsync(d_raw, d_src ? d_src : h_faces6, raw, d_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, launch_cube_pad(d_raw, res, d_pad8, d_pad, d_cells, s));
+    DevBuf d_raw, d_pad8, d_pad, d_cells;
+    CU_TRY(ctx, d_raw.alloc(raw));
+    CU_TRY(ctx, d_pad8.alloc(pad));
+    CU_TRY(ctx, d_pad.alloc(pad * sizeof(float)));
+    CU_TRY(ctx, d_cells.alloc(size_t(6) * (res + 1) * (res + 1) * sizeof(float4)));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw.p, d_src ? d_src : h_faces6, raw, d_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, launch_cube_pad(d_raw.as<uint8_t>(), res, d_pad8.as<uint8_t>(), d_pad.as<float>(), d_cells.as<float4>(), s));
     ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
-    cudaFree(ctx->d_cube_raw);
     cudaFree(ctx->d_cube_pad_u8);
-    cudaFree(ctx->d_cube_pad);
     cudaFree(ctx->d_cube_cells);
-    ctx->d_cube_raw = d_raw;
-    ctx->d_cube_pad_u8 = d_pad8;
-    ctx->d_cube_pad = d_pad;
-    ctx->d_cube_cells = d_cells;
+    ctx->d_cube_pad_u8 = d_pad8.release<uint8_t>();
+    ctx->d_cube_cells = d_cells.release<float4>();
     ctx->cube_res = res;
     return B200ATMO_OK;
 }
 
 int upload_shape(b200atmo_ctx* ctx, const uint8_t* h, int nx, int ny, int nz, cudaStream_t s) {
     const size_t raw = size_t(nx) * ny * nz, pad = size_t(nx + 2) * (ny + 2) * (nz + 2);
-    uint8_t* d_raw = nullptr;
-    float* d_pad = nullptr;
-    float4* d_cells = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d_raw, raw));
-    CU_TRY(ctx, cudaMalloc(&d_pad, pad * sizeof(float)));
-    CU_TRY(ctx, cudaMalloc(&d_cells, size_t(nx + 1) * (ny + 1) * (nz + 1) * 2 * sizeof(float4)));
-    CU_TRY(ctx, cudaMemcpyAsync(d_raw, h, raw, cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, launch_shape_pad(d_raw, nx, ny, nz, d_pad, d_cells, s));
+    DevBuf d_raw, d_pad, d_cells;
+    CU_TRY(ctx, d_raw.alloc(raw));
+    CU_TRY(ctx, d_pad.alloc(pad * sizeof(float)));
+    CU_TRY(ctx, d_cells.alloc(size_t(nx + 1) * (ny + 1) * (nz + 1) * 2 * sizeof(float4)));
+    CU_TRY(ctx, cudaMemcpyAsync(d_raw.p, h, raw, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, launch_shape_pad(d_raw.as<uint8_t>(), nx, ny, nz, d_pad.as<float>(), d_cells.as<float4>(), s));
     ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
-    cudaFree(ctx->d_shape_raw);
-    cudaFree(ctx->d_shape_pad);
     cudaFree(ctx->d_shape_cells);
-    ctx->d_shape_raw = d_raw;
-    ctx->d_shape_pad = d_pad;
-    ctx->d_shape_cells = d_cells;
+    ctx->d_shape_cells = d_cells.release<float4>();
     ctx->nx = nx;
     ctx->ny = ny;
     ctx->nz = nz;
@@ -249,13 +250,9 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
     cudaFree(ctx->d_lut_cells);
-    cudaFree(ctx->d_cube_raw);
     cudaFree(ctx->d_cube_pad_u8);
-    cudaFree(ctx->d_cube_pad);
     cudaFree(ctx->d_cube_cells);
     cudaFree(ctx->d_shape_cells);
-    cudaFree(ctx->d_shape_raw);
-    cudaFree(ctx->d_shape_pad);
     cudaFree(ctx->d_blue);
     cudaFree(ctx->d_stage_in0);
     cudaFree(ctx->d_stage_in1);
@@ -306,11 +303,11 @@ int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w
     if (!is_pow2(w) || !is_pow2(h) || w > 4096 || h > 4096)
         return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: sizes must be powers of two <= 4096");
     DeviceGuard g(ctx->device);
-    uint8_t* d = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d, size_t(w) * h));
-    CU_TRY(ctx, cudaMemcpy(d, h_texels, size_t(w) * h, cudaMemcpyHostToDevice));
+    DevBuf d;
+    CU_TRY(ctx, d.alloc(size_t(w) * h));
+    CU_TRY(ctx, cudaMemcpy(d.p, h_texels, size_t(w) * h, cudaMemcpyHostToDevice));
     cudaFree(ctx->d_blue);
-    ctx->d_blue = d;
+    ctx->d_blue = d.release<uint8_t>();
     ctx->bn_w = w;
     ctx->bn_h = h;
     return B200ATMO_OK;
@@ -340,17 +337,13 @@ int b200atmo_generate_noise_cubemap(b200atmo_ctx* ctx, const B200AtmoNoise* nois
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->streams[0];
     const size_t raw = size_t(6) * res * res;
-    uint8_t* d_faces = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d_faces, raw));
-    cudaError_t e = launch_noise_cube(*noise, scale, res, d_faces, s);
+    DevBuf d_faces;
+    CU_TRY(ctx, d_faces.alloc(raw));
+    CU_TRY(ctx, launch_noise_cube(*noise, scale, res, d_faces.as<uint8_t>(), s));
     ctx->launches++;
-    if (e == cudaSuccess && h_faces6_out) e = cudaMemcpyAsync(h_faces6_out, d_faces, raw, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    int rc = B200ATMO_OK;
-    if (e != cudaSuccess) rc = fail(ctx, B200ATMO_E_CUDA, std::string("noise cubemap: ") + cudaGetErrorString(e));
-    else if (set_as_coverage) rc = upload_cube(ctx, nullptr, res, s, d_faces);
-    cudaFree(d_faces);
-    return rc;
+    if (h_faces6_out) CU_TRY(ctx, cudaMemcpyAsync(h_faces6_out, d_faces.p, raw, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    return set_as_coverage ? upload_cube(ctx, nullptr, res, s, d_faces.as<uint8_t>()) : B200ATMO_OK;
 }
 
 int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream) {
@@ -454,9 +447,7 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
     int rc = frame_consts(ctx, cam, w, h, row_begin, row_end, c);
     if (rc != B200ATMO_OK) return rc;
     if (row_begin == row_end) return B200ATMO_OK;
-    if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
-    consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));  // LUT pointer is stable; refresh anyway
-    consts_set_camera(c, ctx->params, *cam, w, h, row_begin, row_end);
+    if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;   // LUT buffers are allocated once: pointers in c stay valid
     RayIO io{};
     io.depth = d_depth;
     io.rgba = d_rgba;

@@ -390,8 +390,16 @@ class PlanetAtmosphere:
             s = self._sun_path
             pos = np.asarray(s.global_transform, dtype=np.float64)[:3, 3] if hasattr(s, "global_transform") else np.asarray(s)
             self._p.sun_position[:] = tuple(float(x) for x in pos)
-        # :335-336
-        self._p.world_to_model[:] = flat_colmajor(np.linalg.inv(np.asarray(self.global_transform, dtype=np.float64)))
+        # :335-336 — Transform3D.inverse(): transposed basis and -B^T * origin (Godot assumes an orthonormal basis there;
+        # the node is never scaled, :315). Same arithmetic as the C++ core (csrc/node/planet_atmosphere_node.cpp).
+        g = np.asarray(self.global_transform, dtype=np.float32)
+        w2m = np.eye(4, dtype=np.float32)
+        w2m[:3, :3] = g[:3, :3].T
+        o = g[:3, 3].astype(np.float64)
+        for r in range(3):
+            b = w2m[r, :3].astype(np.float64)
+            w2m[r, 3] = np.float32(-(b[0] * o[0] + b[1] * o[1] + b[2] * o[2]))
+        self._p.world_to_model[:] = flat_colmajor(w2m)
         # :339-341 — Transform2D().rotated(a): columns (cos, sin), (-sin, cos)
         t = (time.monotonic() - self._t0) if now is None else float(now)
         a = t * math.radians(self.clouds_rotation_speed)

@@ -23,6 +23,7 @@ EXPORTS = [
     "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube", "b200atmo_generate_noise_cubemap",
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
+    "b200atmo_render_frame_host_submit", "b200atmo_frame_wait",
     "b200atmo_launch_count",
 ]
 
@@ -68,6 +69,8 @@ def lib():
         L.b200atmo_render_frame_composite.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, vp]
         L.b200atmo_make_rays.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, C.POINTER(B200AtmoFrame), vp]
         L.b200atmo_render_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp]
+        L.b200atmo_render_frame_host_submit.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, i32]
+        L.b200atmo_frame_wait.argtypes = [vp, i32]
         L.b200atmo_launch_count.argtypes = [vp]
         L.b200atmo_launch_count.restype = C.c_uint64
         for name in EXPORTS:
@@ -204,6 +207,14 @@ class AtmosphereContext:
     def render_frame_host(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None):
         self._check(lib().b200atmo_render_frame_host(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
                                                      _dptr(discard)))
+
+    def render_frame_host_submit(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, slot=0):
+        """Pipelined host-buffer frame: returns after enqueueing; `frame_wait(slot)` completes it."""
+        self._check(lib().b200atmo_render_frame_host_submit(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
+                                                            _dptr(discard), int(slot)))
+
+    def frame_wait(self, slot=0):
+        self._check(lib().b200atmo_frame_wait(self._h, int(slot)))
 
     @property
     def launch_count(self) -> int:

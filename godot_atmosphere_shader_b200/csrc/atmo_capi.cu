@@ -36,6 +36,16 @@ struct b200atmo_ctx {
     uint8_t* d_stage_disc = nullptr;
     size_t cap_in0 = 0, cap_in1 = 0, cap_out = 0, cap_disc = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
+    // pipelined host-buffer frames (b200atmo_render_frame_host_submit / b200atmo_frame_wait): per slot its own stream
+    // and device staging, so the D2H of frame k overlaps the H2D + kernel of frame k+1
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        void* d_depth = nullptr;
+        void* d_rgba = nullptr;
+        void* d_disc = nullptr;
+        size_t cap_depth = 0, cap_rgba = 0, cap_disc = 0;
+        bool in_flight = false;
+    } slots[B200ATMO_PIPELINE_SLOTS];
     uint64_t launches = 0;
     std::string last_error;
 };
@@ -98,8 +108,21 @@ DeviceTextures textures_of(const b200atmo_ctx* ctx) {
     return t;
 }
 
+// Frames submitted with b200atmo_render_frame_host_submit read the LUT / textures asynchronously: anything that rewrites
+// or frees those buffers waits for them first (rare paths: re-bake, texture upload, destroy).
+int drain_slots(b200atmo_ctx* ctx) {
+    for (auto& sl : ctx->slots) {
+        if (!sl.in_flight) continue;
+        CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
+        sl.in_flight = false;
+    }
+    return B200ATMO_OK;
+}
+
 int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
     if (!ctx->lut_stale) return B200ATMO_OK;
+    int drained = drain_slots(ctx);
+    if (drained != B200ATMO_OK) return drained;
     CU_TRY(ctx, launch_bake_lut(ctx->params.planet_radius, ctx->params.atmosphere_height, ctx->params.density, ctx->d_lut,
                                 ctx->d_lut_pad, ctx->d_lut_cells, s));
     ctx->launches += 2;
@@ -129,6 +152,8 @@ struct DevBuf {
 // b200atmo_download_cube_padded) and the cells the kernels sample
 int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_t s, const uint8_t* d_src = nullptr) {
     const size_t raw = size_t(6) * res * res, pad = size_t(6) * (res + 2) * (res + 2);
+    int drained = drain_slots(ctx);
+    if (drained != B200ATMO_OK) return drained;
     DevBuf d_raw, d_pad8, d_pad, d_cells;
     CU_TRY(ctx, d_raw.alloc(raw));
     CU_TRY(ctx, d_pad8.alloc(pad));
@@ -148,6 +173,8 @@ int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_
 
 int upload_shape(b200atmo_ctx* ctx, const uint8_t* h, int nx, int ny, int nz, cudaStream_t s) {
     const size_t raw = size_t(nx) * ny * nz, pad = size_t(nx + 2) * (ny + 2) * (nz + 2);
+    int drained = drain_slots(ctx);
+    if (drained != B200ATMO_OK) return drained;
     DevBuf d_raw, d_pad, d_cells;
     CU_TRY(ctx, d_raw.alloc(raw));
     CU_TRY(ctx, d_pad.alloc(pad * sizeof(float)));
@@ -234,6 +261,7 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
     CREATE_TRY(cudaMalloc(&ctx->d_lut_cells, sizeof(float4) * kLutCells * kLutCells));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[0], cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[1], cudaStreamNonBlocking));
+    for (auto& sl : ctx->slots) CREATE_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
 #undef CREATE_TRY
     // unset samplers read as white (README.md:46: "by default they cover the whole atmosphere uniformly")
     const uint8_t white[6] = {255, 255, 255, 255, 255, 255};
@@ -247,6 +275,15 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
 void b200atmo_destroy(b200atmo_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
+    for (auto& sl : ctx->slots) {
+        if (sl.stream) {
+            cudaStreamSynchronize(sl.stream);
+            cudaStreamDestroy(sl.stream);
+        }
+        cudaFree(sl.d_depth);
+        cudaFree(sl.d_rgba);
+        cudaFree(sl.d_disc);
+    }
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
     cudaFree(ctx->d_lut_cells);
@@ -560,6 +597,47 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
+                                      float* h_rgba, uint8_t* h_discard, int slot) {
+    if (!ctx || !cam || !h_depth || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: NULL argument");
+    if (w < 1 || h < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: bad size");
+    if (slot < 0 || slot >= B200ATMO_PIPELINE_SLOTS) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: bad slot");
+    b200atmo_ctx::Slot& sl = ctx->slots[slot];
+    if (sl.in_flight) return fail(ctx, B200ATMO_E_STATE, "b200atmo_render_frame_host_submit: slot still in flight (call b200atmo_frame_wait)");
+    DeviceGuard g(ctx->device);
+    const size_t npx = size_t(w) * h;
+    int rc;
+    if ((rc = ensure(ctx, &sl.d_depth, &sl.cap_depth, npx * sizeof(float))) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &sl.d_rgba, &sl.cap_rgba, npx * 4 * sizeof(float))) != B200ATMO_OK) return rc;
+    if (h_discard && (rc = ensure(ctx, &sl.d_disc, &sl.cap_disc, npx)) != B200ATMO_OK) return rc;
+    if ((rc = bake_if_stale(ctx, sl.stream)) != B200ATMO_OK) return rc;
+    DevConsts c;   // uniforms, variant and camera are captured here (kernel parameter space)
+    if ((rc = frame_consts(ctx, cam, w, h, 0, h, c)) != B200ATMO_OK) return rc;
+    RayIO io{};
+    io.depth = static_cast<float*>(sl.d_depth);
+    io.rgba = sl.d_rgba;
+    io.discard = h_discard ? static_cast<uint8_t*>(sl.d_disc) : nullptr;
+    io.n = npx;
+    CU_TRY(ctx, cudaMemcpyAsync(sl.d_depth, h_depth, npx * sizeof(float), cudaMemcpyHostToDevice, sl.stream));
+    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, sl.stream));
+    ctx->launches++;
+    sl.in_flight = true;
+    CU_TRY(ctx, cudaMemcpyAsync(h_rgba, sl.d_rgba, npx * 4 * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard, sl.d_disc, npx, cudaMemcpyDeviceToHost, sl.stream));
+    return B200ATMO_OK;
+}
+
+int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot) {
+    if (!ctx) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_frame_wait: NULL context");
+    if (slot < 0 || slot >= B200ATMO_PIPELINE_SLOTS) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_frame_wait: bad slot");
+    b200atmo_ctx::Slot& sl = ctx->slots[slot];
+    if (!sl.in_flight) return B200ATMO_OK;
+    DeviceGuard g(ctx->device);
+    sl.in_flight = false;
+    CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
     return B200ATMO_OK;
 }
 

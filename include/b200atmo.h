@@ -225,6 +225,21 @@ int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float
 int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
                                int w, int h, float* h_rgba, uint8_t* h_discard);
 
+/*
+ * Pipelined form of b200atmo_render_frame_host for a stream of frames (one per _process tick, or the tiles of an
+ * offscreen target): enqueues H2D(depth) -> render -> D2H(rgba [, discard]) on pipeline slot `slot` and returns without
+ * waiting; b200atmo_frame_wait(ctx, slot) blocks until that frame's host buffers are complete. Each slot owns a stream
+ * and device staging, so while frame k downloads (the PCIe-bound leg: 16 B/pixel), frame k+1 on the other slot uploads
+ * and renders. Uniforms, variant and camera are captured at submit time. The host buffers must stay valid (and should be
+ * pinned) until the wait returns; a slot must be waited on before it is submitted again (B200ATMO_E_STATE otherwise).
+ * Texture uploads, re-bakes and b200atmo_destroy wait for frames in flight themselves.
+ * Results are bit-identical to b200atmo_render_frame_host.
+ */
+#define B200ATMO_PIPELINE_SLOTS 2
+int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
+                                      int w, int h, float* h_rgba, uint8_t* h_discard, int slot);
+int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot);
+
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */
 uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx);
 

@@ -247,6 +247,62 @@ def test_frame_api_equals_ray_api_and_host_api(cuda_ctx_factory):
     assert np.array_equal(he, hc) and np.array_equal(hf, hd)
 
 
+def test_pipelined_host_frames_equal_the_synchronous_call(cuda_ctx_factory):
+    """b200atmo_render_frame_host_submit / b200atmo_frame_wait: 6 frames (orbiting camera, uniforms changed between
+    submits) over the two slots are bit-identical to b200atmo_render_frame_host; slot state errors are reported."""
+    torch = _torch()
+    from godot_atmosphere_shader_b200.context import B200AtmoError
+    ctx = cuda_ctx_factory()
+    w, h = 256, 144
+    p = scenes.demo_params()
+    _setup(ctx, p, VARIANTS["clouds"])
+    frames = []
+    for k in range(6):
+        cam = scenes.camera_a(w, h, orbit_deg=20.0 * k)
+        depth = torch.from_numpy(scenes.synth_depth(cam, p, w, h)).pin_memory()
+        frames.append((cam, depth, torch.empty((h * w, 4), dtype=torch.float32).pin_memory(),
+                       torch.empty((h * w,), dtype=torch.uint8).pin_memory()))
+    strengths = [1.0, 0.5, 2.0, 1.0, 3.0, 0.25]
+    for k, (cam, depth, rgba, disc) in enumerate(frames):
+        slot = k & 1
+        ctx.frame_wait(slot)                      # no-op the first time round
+        q = p.copy()
+        q.scattering_strength = strengths[k]     # captured at submit time
+        ctx.set_params(q)
+        ctx.render_frame_host_submit(cam, depth, w, h, rgba, disc, slot=slot)
+    with pytest.raises(B200AtmoError) as ei:      # slot 1 still holds frame 5
+        ctx.render_frame_host_submit(frames[0][0], frames[0][1], w, h, frames[0][2], None, slot=1)
+    assert ei.value.code == abi.E_STATE
+    with pytest.raises(B200AtmoError):
+        ctx.frame_wait(2)
+    ctx.frame_wait(0)
+    ctx.frame_wait(1)
+    ctx.frame_wait(1)                             # idempotent
+    want = np.empty((h * w, 4), np.float32)
+    wdisc = np.empty((h * w,), np.uint8)
+    for k, (cam, depth, rgba, disc) in enumerate(frames):
+        q = p.copy()
+        q.scattering_strength = strengths[k]
+        ctx.set_params(q)
+        ctx.render_frame_host(cam, depth, w, h, want, wdisc)
+        assert np.array_equal(rgba.numpy().view(np.uint32), want.view(np.uint32)), f"frame {k}"
+        assert np.array_equal(disc.numpy(), wdisc)
+    # a texture upload / re-bake while a frame is in flight waits for it instead of racing
+    cam, depth, rgba, disc = frames[0]
+    ctx.set_params(p)
+    ctx.render_frame_host_submit(cam, depth, w, h, rgba, disc, slot=0)
+    ctx.upload_coverage_cube(Hh.demo_textures()[1])
+    q = p.copy()
+    q.density = 0.4
+    ctx.set_params(q)
+    ctx.render_frame_host_submit(cam, depth, w, h, frames[1][2], None, slot=1)   # re-bakes: drains slot 0 first
+    ctx.frame_wait(0)
+    ctx.frame_wait(1)
+    ctx.set_params(p)
+    ctx.render_frame_host(cam, depth, w, h, want, wdisc)
+    assert np.array_equal(rgba.numpy().view(np.uint32), want.view(np.uint32))
+
+
 def test_full_size_properties(cuda_ctx_factory):
     """BASELINE config[1] size (1920x1080, N=32): size-independent properties instead of a full oracle run."""
     torch = _torch()

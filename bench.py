@@ -400,6 +400,17 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / a.e2e_steps
     e2e_ok = e2e_ok and all(bool(np.array_equal(b.numpy(), d_rgba.cpu().numpy())) for b in h_rgbas[:min(2, a.e2e_steps)])
+    # the whole transparent pass against Godot's RGBA16F colour target: depth + colour up, render + blend_mix, colour down
+    from godot_atmosphere_shader_b200 import abi as _abi
+    h_color = torch.zeros((n_rays, 4), dtype=torch.float16).pin_memory()
+    for _ in range(3):
+        ctx.composite_frame_host(cam, h_depth, w, h, h_color, color_format=_abi.COLOR_RGBA16F)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        ctx.composite_frame_host(cam, h_depth, w, h, h_color, color_format=_abi.COLOR_RGBA16F)
+    torch.cuda.synchronize()
+    comp_s = (time.perf_counter() - t0) / a.e2e_steps
     te = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -433,6 +444,9 @@ def run_ours(a, rank, world, local_rank):
                 "timer": "host perf_counter around the whole loop incl. the final waits", "matches_device_path": e2e_ok,
                 "synchronous": {"value": world * ray_steps / e2e_sync_s, "ms_per_step": e2e_sync_s * 1e3,
                                 "api": "b200atmo_render_frame_host (one frame at a time, 4 row bands over 2 streams)"}},
+        "e2e_composite_rgba16f": {"ms_per_step": comp_s * 1e3, "value": ray_steps / comp_s, "unit": UNIT,
+                                  "h2d_bytes_per_step": n_rays * 12, "d2h_bytes_per_step": n_rays * 8,
+                                  "api": "b200atmo_composite_frame_host (rank 0; fp32 render + blend_mix into an RGBA16F frame)"},
         "gpu_launches": launches,
         "frame_api": {"ms_per_step": frame_ms, "value": world * ray_steps / (frame_ms * 1e-3), "unit": UNIT,
                       "api": "b200atmo_render_frame (device depth in, 4 B + 16 B per pixel)", "bit_identical_to_ray_api": frame_ok},

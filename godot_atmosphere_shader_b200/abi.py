@@ -20,6 +20,9 @@ LIGHT_NONE = 0
 LIGHT_CHEAP = 1
 LIGHT_RAYMARCHED = 2
 
+COLOR_RGBA32F = 0
+COLOR_RGBA16F = 1
+
 
 class B200AtmoParams(C.Structure):
     """Shader uniform set, SURVEY.md §8(b2). Names are the reference's uniform names minus `u_`."""

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import abi
-from .abi import B200AtmoCamera, B200AtmoFrame, B200AtmoParams
+from .abi import COLOR_RGBA32F, B200AtmoCamera, B200AtmoFrame, B200AtmoParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200ATMO_LIB", os.path.join(_HERE, "libb200atmo.so"))  # override: kernel-tuning builds only
@@ -23,7 +23,7 @@ EXPORTS = [
     "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube", "b200atmo_generate_noise_cubemap",
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
-    "b200atmo_render_frame_host_submit", "b200atmo_frame_wait",
+    "b200atmo_render_frame_host_submit", "b200atmo_frame_wait", "b200atmo_render_frame_composite_fmt", "b200atmo_composite_frame_host",
     "b200atmo_launch_count",
 ]
 
@@ -71,6 +71,8 @@ def lib():
         L.b200atmo_render_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp]
         L.b200atmo_render_frame_host_submit.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, i32]
         L.b200atmo_frame_wait.argtypes = [vp, i32]
+        L.b200atmo_render_frame_composite_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp]
+        L.b200atmo_composite_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32]
         L.b200atmo_launch_count.argtypes = [vp]
         L.b200atmo_launch_count.restype = C.c_uint64
         for name in EXPORTS:
@@ -193,10 +195,17 @@ class AtmosphereContext:
         self._check(lib().b200atmo_render_frame(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
                                                 int(h if row_end is None else row_end), _dptr(rgba), _dptr(discard), stream))
 
-    def render_frame_composite(self, cam: B200AtmoCamera, depth, w, h, color_inout, row_begin=0, row_end=None, stream=None):
-        """Render and alpha-blend into the frame's colour buffer (float4 per pixel) like the ROP's blend_mix."""
-        self._check(lib().b200atmo_render_frame_composite(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
-                                                          int(h if row_end is None else row_end), _dptr(color_inout), stream))
+    def render_frame_composite(self, cam: B200AtmoCamera, depth, w, h, color_inout, row_begin=0, row_end=None, stream=None,
+                               color_format=COLOR_RGBA32F):
+        """Render and alpha-blend into the frame's colour buffer (float4 or half4 per pixel) like the ROP's blend_mix."""
+        self._check(lib().b200atmo_render_frame_composite_fmt(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
+                                                              int(h if row_end is None else row_end), _dptr(color_inout),
+                                                              int(color_format), stream))
+
+    def composite_frame_host(self, cam: B200AtmoCamera, depth, w, h, color_inout, color_format=COLOR_RGBA32F):
+        """Host buffers: depth + colour up, render + blend, colour down (in place)."""
+        self._check(lib().b200atmo_composite_frame_host(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(color_inout),
+                                                        int(color_format)))
 
     def make_rays(self, cam: B200AtmoCamera, depth, w, h, origin_depth, dir_jitter, stream=None) -> B200AtmoFrame:
         fr = B200AtmoFrame()

@@ -495,10 +495,12 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
     return B200ATMO_OK;
 }
 
-int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
-                                    int row_begin, int row_end, float* d_color_inout, void* stream) {
+int b200atmo_render_frame_composite_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                        int row_begin, int row_end, void* d_color_inout, int color_format, void* stream) {
     if (!ctx || !cam || !d_depth || !d_color_inout)
         return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_composite: NULL argument");
+    if (color_format != B200ATMO_COLOR_RGBA32F && color_format != B200ATMO_COLOR_RGBA16F)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_composite: unknown colour format");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = bake_if_stale(ctx, s);
@@ -509,9 +511,59 @@ int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam
     RayIO io{};
     io.depth = d_depth;
     io.color_inout = d_color_inout;
+    io.color_format = color_format;
     io.n = size_t(w) * h;
     CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                    int row_begin, int row_end, float* d_color_inout, void* stream) {
+    return b200atmo_render_frame_composite_fmt(ctx, cam, d_depth, w, h, row_begin, row_end, d_color_inout, B200ATMO_COLOR_RGBA32F,
+                                               stream);
+}
+
+int b200atmo_composite_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
+                                  void* h_color_inout, int color_format) {
+    if (!ctx || !cam || !h_depth || !h_color_inout) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_composite_frame_host: NULL argument");
+    if (w < 1 || h < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_composite_frame_host: bad size");
+    if (color_format != B200ATMO_COLOR_RGBA32F && color_format != B200ATMO_COLOR_RGBA16F)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_composite_frame_host: unknown colour format");
+    DeviceGuard g(ctx->device);
+    const size_t npx = size_t(w) * h, px_bytes = color_format == B200ATMO_COLOR_RGBA16F ? 8 : 16;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_in0, &ctx->cap_in0, npx * sizeof(float))) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, npx * px_bytes)) != B200ATMO_OK) return rc;
+    if ((rc = bake_if_stale(ctx, ctx->streams[0])) != B200ATMO_OK) return rc;
+    float* d_depth = static_cast<float*>(ctx->d_stage_in0);
+    char* d_color = static_cast<char*>(ctx->d_stage_out);
+    char* h_color = static_cast<char*>(h_color_inout);
+    DevConsts c;
+    if ((rc = frame_consts(ctx, cam, w, h, 0, h, c)) != B200ATMO_OK) return rc;
+    RayIO io{};
+    io.depth = d_depth;
+    io.color_inout = d_color;
+    io.color_format = color_format;
+    io.n = npx;
+    // equal row bands alternating over two streams: the uploads of band k+1 (12 or 20 B/pixel) run while band k downloads
+    // (8 or 16 B/pixel); PCIe is full duplex, so the slower direction bounds the frame
+    const int bands = h >= 512 ? 8 : (h >= 256 ? 4 : 1);   // the upload is the longer leg here: finer bands shorten the tail
+    for (int k = 0; k < bands; ++k) {
+        const int r0 = int(int64_t(h) * k / bands), r1 = int(int64_t(h) * (k + 1) / bands);
+        if (r1 <= r0) continue;
+        cudaStream_t s = ctx->streams[k & 1];
+        const size_t off = size_t(r0) * w, cnt = size_t(r1 - r0) * w;
+        CU_TRY(ctx, cudaMemcpyAsync(d_depth + off, h_depth + off, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU_TRY(ctx, cudaMemcpyAsync(d_color + off * px_bytes, h_color + off * px_bytes, cnt * px_bytes, cudaMemcpyHostToDevice, s));
+        c.row_begin = r0;
+        c.row_end = r1;
+        CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+        ctx->launches++;
+        CU_TRY(ctx, cudaMemcpyAsync(h_color + off * px_bytes, d_color + off * px_bytes, cnt * px_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
     return B200ATMO_OK;
 }
 

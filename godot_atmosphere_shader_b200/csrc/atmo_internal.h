@@ -69,7 +69,8 @@ struct RayIO {
     const void* dir_jitter;    // float4[n]
     const float* depth;        // float[w*h]  frame in
     void* rgba;                // float4[...] out
-    void* color_inout;         // float4[w*h] frame colour buffer to blend into (frame kernel; then rgba may be null)
+    void* color_inout;         // frame colour buffer to blend into (frame kernel; then rgba may be null): float4[w*h] or half4[w*h]
+    int color_format;          // B200ATMO_COLOR_RGBA32F / B200ATMO_COLOR_RGBA16F
     uint8_t* discard;          // nullable
     void* out_origin_depth;    // make_rays only
     void* out_dir_jitter;

@@ -1,5 +1,6 @@
 // sm_100a kernels of the atmosphere hot path + their launchers. Compile with -fmad=false (see the
 // numeric policy in atmo_device.cuh).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "atmo_device.cuh"
@@ -232,10 +233,21 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
         disc = shade_ray<MODEL, LIGHT>(c, o, d, linear_depth, jitter, out);
     if (io.color_inout) {  // the ROP's blend_mix of an unshaded spatial shader, exact arithmetic; discard = no write
         if (!disc) {
-            float4* dst = static_cast<float4*>(io.color_inout) + i;
-            const float4 bg = *dst;
             const float ia = 1.0f - out.w;
-            *dst = make_float4(out.x * out.w + bg.x * ia, out.y * out.w + bg.y * ia, out.z * out.w + bg.z * ia, bg.w);
+            if (io.color_format == B200ATMO_COLOR_RGBA16F) {
+                // the Forward+ 3D colour target: blended in fp32, stored round-to-nearest-even like the ROP; alpha bits untouched
+                uint2* dst = static_cast<uint2*>(io.color_inout) + i;
+                const uint2 raw = *dst;
+                const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float b = __half2float(__ushort_as_half((unsigned short)(raw.y & 0xffffu)));
+                const __half2 o_rg = __floats2half2_rn(out.x * out.w + rg.x * ia, out.y * out.w + rg.y * ia);
+                const unsigned o_b = __half_as_ushort(__float2half_rn(out.z * out.w + b * ia));
+                *dst = make_uint2(*reinterpret_cast<const unsigned*>(&o_rg), (raw.y & 0xffff0000u) | o_b);
+            } else {
+                float4* dst = static_cast<float4*>(io.color_inout) + i;
+                const float4 bg = *dst;
+                *dst = make_float4(out.x * out.w + bg.x * ia, out.y * out.w + bg.y * ia, out.z * out.w + bg.z * ia, bg.w);
+            }
         }
     } else {
         __stcs(static_cast<float4*>(io.rgba) + i, out);

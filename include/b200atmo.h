@@ -217,6 +217,20 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
  * d_color_inout: w*h float4 (linear HDR colour), rows [row_begin,row_end) are updated in place. */
 int b200atmo_render_frame_composite(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
                                     int row_begin, int row_end, float* d_color_inout, void* stream);
+/* Same, for either colour-buffer format. Godot's Forward+ renderer keeps the 3D colour target in RGBA16F: the blend is
+ * computed in fp32 from the fp32 ALBEDO/ALPHA and the stored value is rounded to nearest-even, as the ROP does; the
+ * destination alpha bits are left untouched. d_color_inout: w*h float4 (RGBA32F) or w*h half4 (RGBA16F). */
+enum {
+    B200ATMO_COLOR_RGBA32F = 0,
+    B200ATMO_COLOR_RGBA16F = 1
+};
+int b200atmo_render_frame_composite_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                        int row_begin, int row_end, void* d_color_inout, int color_format, void* stream);
+/* HOST-buffer variant, the whole transparent pass of the reference in one call: H2D depth + colour, render + blend,
+ * D2H colour (in place in h_color_inout); synchronous. RGBA16F moves 4 + 8 B/pixel up and 8 B/pixel down (the
+ * un-blended b200atmo_render_frame_host: 4 up, 16 down). */
+int b200atmo_composite_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
+                                  void* h_color_inout, int color_format);
 /* Frame front-end only (main:101-103,128-142): depth buffer -> the SoA ray buffers of the ray-batch API and
  * the frame constants that go with them (frame_out may be NULL). */
 int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,

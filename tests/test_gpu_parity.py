@@ -502,6 +502,27 @@ def test_composite_equals_render_then_blend(cuda_ctx_factory):
     want[d == 1] = bg[d == 1]
     assert np.array_equal(color.cpu().numpy().view(np.uint32), want.view(np.uint32))
     assert (d == 1).any() and (d == 0).any()
+    # RGBA16F colour target (Godot Forward+): fp32 blend, round-to-nearest-even store, alpha bits untouched
+    bg16 = rng.uniform(0, 4, size=(h, w, 4)).astype(np.float16)
+    bg16[0, 0] = np.array([65504.0, 6e-8, 0.0, -1.0], dtype=np.float16)   # max finite, subnormal
+    color16 = torch.from_numpy(bg16.copy()).cuda()
+    ctx.render_frame_composite(cam, d_depth, w, h, color16, color_format=abi.COLOR_RGBA16F)
+    torch.cuda.synchronize()
+    b32 = bg16.astype(np.float32)
+    want16 = bg16.copy()
+    want16[..., :3] = (src[..., :3] * a + b32[..., :3] * (np.float32(1.0) - a)).astype(np.float16)
+    want16[d == 1] = bg16[d == 1]
+    assert np.array_equal(color16.cpu().numpy().view(np.uint16), want16.view(np.uint16))
+    # host-buffer form, both formats
+    hc16 = bg16.copy()
+    ctx.composite_frame_host(cam, depth, w, h, hc16, color_format=abi.COLOR_RGBA16F)
+    assert np.array_equal(hc16.view(np.uint16), want16.view(np.uint16))
+    hc32 = bg.copy()
+    ctx.composite_frame_host(cam, depth, w, h, hc32)
+    assert np.array_equal(hc32.view(np.uint32), want.view(np.uint32))
+    from godot_atmosphere_shader_b200.context import B200AtmoError
+    with pytest.raises(B200AtmoError):
+        ctx.composite_frame_host(cam, depth, w, h, hc32, color_format=7)
 
 
 def test_garbage_uniforms_never_fault(cuda_ctx_factory):

@@ -273,22 +273,14 @@ void B200AtmosphereEffect::_render_callback(int32_t, RenderData* p_render_data) 
     const PackedByteArray depth_bytes = rd->texture_get_data(buffers->get_depth_layer(0), 0);   // R32_SFLOAT, reverse-Z
     if (depth_bytes.size() != int64_t(w) * h * 4) return;
     depth_.resize(size_t(w) * h);
-    rgba_.resize(size_t(w) * h * 4);
     std::memcpy(depth_.data(), depth_bytes.ptr(), depth_bytes.size());
-    if (owner_->core()->render_host(cam, depth_.data(), w, h, rgba_.data(), nullptr) != B200ATMO_OK) {
+    // render_mode unshaded + blend_mix (planet_atmosphere_*.gdshader:2) straight into the RGBA16F 3D colour target:
+    // depth + colour up, fp32 render + blend on the GPU, colour down (b200atmo_composite_frame_host)
+    PackedByteArray color = rd->texture_get_data(buffers->get_color_layer(0), 0);
+    if (color.size() != int64_t(w) * h * 8) return;
+    if (owner_->core()->composite_host(cam, depth_.data(), w, h, color.ptrw(), B200ATMO_COLOR_RGBA16F) != B200ATMO_OK) {
         UtilityFunctions::push_error(String(owner_->core()->last_error().c_str()));
         return;
-    }
-    // render_mode unshaded + blend_mix (planet_atmosphere_*.gdshader:2): color = albedo*alpha + color*(1-alpha);
-    // the 3D colour buffer of Forward+ is RGBA16F
-    PackedByteArray color = rd->texture_get_data(buffers->get_color_layer(0), 0);
-    uint16_t* px = reinterpret_cast<uint16_t*>(color.ptrw());
-    for (size_t i = 0; i < size_t(w) * h; ++i) {
-        const float a = rgba_[4 * i + 3];
-        for (int k = 0; k < 3; ++k) {
-            const float dst = Math::half_to_float(px[4 * i + k]);
-            px[4 * i + k] = Math::make_half_float(rgba_[4 * i + k] * a + dst * (1.0f - a));
-        }
     }
     rd->texture_update(buffers->get_color_layer(0), 0, color);
 }

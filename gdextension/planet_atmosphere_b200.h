@@ -31,7 +31,7 @@ protected:
 
 private:
     PlanetAtmosphereB200* owner_ = nullptr;
-    std::vector<float> depth_, rgba_;
+    std::vector<float> depth_;
 };
 
 class PlanetAtmosphereB200 : public godot::Node3D {

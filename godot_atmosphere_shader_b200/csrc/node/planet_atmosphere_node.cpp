@@ -14,7 +14,7 @@ const Api& linked_api() {
         b200atmo_create,        b200atmo_destroy,        b200atmo_last_error,          b200atmo_default_params,
         b200atmo_set_params,    b200atmo_set_variant,    b200atmo_upload_blue_noise,   b200atmo_upload_shape3d,
         b200atmo_upload_coverage_cube, b200atmo_bake_optical_depth, b200atmo_render_frame, b200atmo_render_frame_composite,
-        b200atmo_render_frame_host,
+        b200atmo_render_frame_host, b200atmo_composite_frame_host,
     };
     return api;
 }
@@ -555,6 +555,13 @@ int PlanetAtmosphere::render_composite(const B200AtmoCamera& cam, const float* d
 int PlanetAtmosphere::render_host(const B200AtmoCamera& cam, const float* h_depth, int w, int h, float* h_rgba, uint8_t* h_discard) {
     int rc = push_params();
     if (rc == B200ATMO_OK) rc = api_.render_frame_host(ctx_, &cam, h_depth, w, h, h_rgba, h_discard);
+    return rc;
+}
+
+int PlanetAtmosphere::composite_host(const B200AtmoCamera& cam, const float* h_depth, int w, int h, void* h_color_inout,
+                                     int color_format) {
+    int rc = push_params();
+    if (rc == B200ATMO_OK) rc = api_.composite_frame_host(ctx_, &cam, h_depth, w, h, h_color_inout, color_format);
     return rc;
 }
 

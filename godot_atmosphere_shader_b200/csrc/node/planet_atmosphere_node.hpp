@@ -44,6 +44,7 @@ struct Api {
     int (*render_frame)(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, int, int, float*, uint8_t*, void*);
     int (*render_frame_composite)(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, int, int, float*, void*);
     int (*render_frame_host)(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, float*, uint8_t*);
+    int (*composite_frame_host)(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, void*, int);
 };
 const Api& linked_api();
 
@@ -201,6 +202,8 @@ public:
     int render(const B200AtmoCamera& cam, const float* d_depth, int w, int h, float* d_rgba, uint8_t* d_discard, void* stream);
     int render_composite(const B200AtmoCamera& cam, const float* d_depth, int w, int h, float* d_color_inout, void* stream);
     int render_host(const B200AtmoCamera& cam, const float* h_depth, int w, int h, float* h_rgba, uint8_t* h_discard);
+    // the whole transparent pass on host buffers: blends into h_color_inout (B200ATMO_COLOR_RGBA32F / _RGBA16F) in place
+    int composite_host(const B200AtmoCamera& cam, const float* h_depth, int w, int h, void* h_color_inout, int color_format);
     std::string last_error() const;
 
 private:

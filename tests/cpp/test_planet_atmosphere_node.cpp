@@ -89,9 +89,13 @@ static int f_rfh(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, f
     g_calls.push_back({"render_frame_host", {}});
     return 0;
 }
+static int f_cfh(b200atmo_ctx*, const B200AtmoCamera*, const float*, int, int, void*, int fmt) {
+    g_calls.push_back({"composite_frame_host", {fmt, 0, 0, 0}});
+    return 0;
+}
 // default_params is a pure host function of the library (no device work): the real one is used
 static const Api kFake = {f_create, f_destroy, f_last_error, b200atmo_default_params, f_set_params, f_set_variant, f_bn,
-                          f_shape,  f_cube,    f_bake,       f_rf,                    f_rfc,        f_rfh};
+                          f_shape,  f_cube,    f_bake,       f_rf,                    f_rfc,        f_rfh, f_cfh};
 
 static std::vector<std::string> g_log;
 static Logger recording_logger() {
@@ -301,6 +305,8 @@ static void test_process_mode_switch_sun_and_rotation() {
     CHECK(count("set_params") == sp + 1 && g_calls.back().name == "render_frame");
     CHECK(n.render_composite(fc, nullptr, 4, 4, nullptr, nullptr) == B200ATMO_OK && g_calls.back().name == "render_frame_composite");
     CHECK(n.render_host(fc, nullptr, 4, 4, nullptr, nullptr) == B200ATMO_OK && g_calls.back().name == "render_frame_host");
+    CHECK(n.composite_host(fc, nullptr, 4, 4, nullptr, B200ATMO_COLOR_RGBA16F) == B200ATMO_OK &&
+          g_calls.back().name == "composite_frame_host" && g_calls.back().a[0] == B200ATMO_COLOR_RGBA16F);
 }
 
 static void test_create_failure_is_loud() {

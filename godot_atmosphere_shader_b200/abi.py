@@ -80,6 +80,16 @@ class B200AtmoCamera(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class B200AtmoPeerTargets(C.Structure):
+    """Where the fused render + all-gather kernels store: the same symmetric buffer on every rank (include/b200atmo.h)."""
+
+    _fields_ = [("d_rgba_peers", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32), ("d_rgba_multicast", C.c_void_p),
+                ("elem_offset", C.c_uint64)]
+
+
 class B200AtmoNoise(C.Structure):
     """Subset of FastNoiseLite's properties used by the generator (include/b200atmo.h)."""
 

@@ -18,12 +18,13 @@ _lib = None
 
 # every symbol include/b200atmo.h declares
 EXPORTS = [
-    "b200atmo_version", "b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera", "b200atmo_create",
+    "b200atmo_version", "b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera", "b200atmo_sizeof_peer_targets", "b200atmo_create",
     "b200atmo_destroy", "b200atmo_last_error", "b200atmo_default_params", "b200atmo_set_params", "b200atmo_get_params",
     "b200atmo_set_variant", "b200atmo_upload_blue_noise", "b200atmo_upload_shape3d", "b200atmo_upload_coverage_cube", "b200atmo_generate_noise_cubemap",
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
     "b200atmo_render_frame_host_submit", "b200atmo_frame_wait", "b200atmo_render_frame_composite_fmt", "b200atmo_composite_frame_host",
+    "b200atmo_render_frame_peers", "b200atmo_render_rays_peers",
     "b200atmo_launch_count",
 ]
 
@@ -44,7 +45,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
         L.b200atmo_version.restype = i32
-        for f in ("b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera"):
+        for f in ("b200atmo_sizeof_params", "b200atmo_sizeof_frame", "b200atmo_sizeof_camera", "b200atmo_sizeof_peer_targets"):
             getattr(L, f).restype = sz
         L.b200atmo_create.argtypes = [i32, C.POINTER(vp)]
         L.b200atmo_destroy.argtypes = [vp]
@@ -71,6 +72,8 @@ def lib():
         L.b200atmo_render_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp]
         L.b200atmo_render_frame_host_submit.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, i32]
         L.b200atmo_frame_wait.argtypes = [vp, i32]
+        L.b200atmo_render_frame_peers.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, C.POINTER(abi.B200AtmoPeerTargets), vp]
+        L.b200atmo_render_rays_peers.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, C.c_size_t, C.POINTER(abi.B200AtmoPeerTargets), vp]
         L.b200atmo_render_frame_composite_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp]
         L.b200atmo_composite_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32]
         L.b200atmo_launch_count.argtypes = [vp]
@@ -216,6 +219,15 @@ class AtmosphereContext:
     def render_frame_host(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None):
         self._check(lib().b200atmo_render_frame_host(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
                                                      _dptr(discard)))
+
+    def render_frame_peers(self, cam: B200AtmoCamera, depth, w, h, targets, row_begin=0, row_end=None, stream=None):
+        """Fused render + all-gather: rows [row_begin, row_end) go straight into every rank's symmetric buffer."""
+        self._check(lib().b200atmo_render_frame_peers(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
+                                                      int(h if row_end is None else row_end), C.byref(targets), stream))
+
+    def render_rays_peers(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, targets, stream=None):
+        self._check(lib().b200atmo_render_rays_peers(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
+                                                     C.byref(targets), stream))
 
     def render_frame_host_submit(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, slot=0):
         """Pipelined host-buffer frame: returns after enqueueing; `frame_wait(slot)` completes it."""

@@ -199,6 +199,7 @@ int b200atmo_version(void) { return B200ATMO_VERSION; }
 size_t b200atmo_sizeof_params(void) { return sizeof(B200AtmoParams); }
 size_t b200atmo_sizeof_frame(void) { return sizeof(B200AtmoFrame); }
 size_t b200atmo_sizeof_camera(void) { return sizeof(B200AtmoCamera); }
+size_t b200atmo_sizeof_peer_targets(void) { return sizeof(B200AtmoPeerTargets); }
 
 void b200atmo_default_params(B200AtmoParams* p) {
     if (!p) return;
@@ -652,6 +653,61 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     return B200ATMO_OK;
 }
 
+static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIO& io, const char* who) {
+    if (!t) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL targets");
+    if (t->n_peers < 1 || t->n_peers > B200ATMO_MAX_PEERS) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": n_peers out of range");
+    for (int r = 0; r < t->n_peers; ++r) {
+        if (!t->d_rgba_peers[r]) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL peer buffer");
+        io.rgba_peers[r] = t->d_rgba_peers[r];
+    }
+    io.n_peers = t->n_peers;
+    io.rgba_multicast = t->d_rgba_multicast;
+    io.peer_offset = size_t(t->elem_offset);
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                                int row_end, const B200AtmoPeerTargets* targets, void* stream) {
+    if (!ctx || !cam || !d_depth) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_peers: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RayIO io{};
+    int rc = peers_to_io(ctx, targets, io, "b200atmo_render_frame_peers");
+    if (rc != B200ATMO_OK) return rc;
+    DevConsts c;
+    if ((rc = frame_consts(ctx, cam, w, h, row_begin, row_end, c)) != B200ATMO_OK) return rc;
+    if (row_begin == row_end) return B200ATMO_OK;
+    if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
+    io.depth = d_depth;
+    io.n = size_t(w) * h;
+    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
+                               size_t n_rays, const B200AtmoPeerTargets* targets, void* stream) {
+    if (!ctx || !frame) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_peers: NULL ctx/frame");
+    RayIO io{};
+    int rc = peers_to_io(ctx, targets, io, "b200atmo_render_rays_peers");
+    if (rc != B200ATMO_OK) return rc;
+    if (n_rays == 0) return B200ATMO_OK;
+    if (!d_origin_depth || !d_dir_jitter) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_peers: NULL buffer");
+    if (n_rays > (size_t(1) << 38)) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_peers: n_rays too large");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
+    DevConsts c;
+    consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));
+    consts_set_frame(c, ctx->params, frame->planet_center_view, frame->sun_center_view, frame->inv_view);
+    io.origin_depth = d_origin_depth;
+    io.dir_jitter = d_dir_jitter;
+    io.n = n_rays;
+    CU_TRY(ctx, launch_render_rays(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
 int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
                                       float* h_rgba, uint8_t* h_discard, int slot) {
     if (!ctx || !cam || !h_depth || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: NULL argument");
@@ -673,10 +729,10 @@ int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* c
     io.rgba = sl.d_rgba;
     io.discard = h_discard ? static_cast<uint8_t*>(sl.d_disc) : nullptr;
     io.n = npx;
+    sl.in_flight = true;   // from the first enqueue on the host buffers are in use, also if a later enqueue fails
     CU_TRY(ctx, cudaMemcpyAsync(sl.d_depth, h_depth, npx * sizeof(float), cudaMemcpyHostToDevice, sl.stream));
     CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, sl.stream));
     ctx->launches++;
-    sl.in_flight = true;
     CU_TRY(ctx, cudaMemcpyAsync(h_rgba, sl.d_rgba, npx * 4 * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
     if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard, sl.d_disc, npx, cudaMemcpyDeviceToHost, sl.stream));
     return B200ATMO_OK;

@@ -71,6 +71,12 @@ struct RayIO {
     void* rgba;                // float4[...] out
     void* color_inout;         // frame colour buffer to blend into (frame kernel; then rgba may be null): float4[w*h] or half4[w*h]
     int color_format;          // B200ATMO_COLOR_RGBA32F / B200ATMO_COLOR_RGBA16F
+    // fused render + all-gather (b200atmo_render_*_peers): the result goes to the same symmetric buffer on every GPU
+    // instead of `rgba`: one multimem store when the NVLS multicast mapping is given, else one P2P store per peer
+    void* rgba_peers[B200ATMO_MAX_PEERS];
+    void* rgba_multicast;
+    int n_peers;               // 0 = plain local store to `rgba`
+    size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
     uint8_t* discard;          // nullable
     void* out_origin_depth;    // make_rays only
     void* out_dir_jitter;

@@ -202,6 +202,21 @@ cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], 
 #endif
 constexpr int kBlock = B200ATMO_BLOCK;
 
+// Result store. Multi-GPU shards write straight into every rank's copy of a symmetric buffer over NVLink: with the NVLS
+// multicast mapping one 16-byte store is replicated by the NVSwitch to all GPUs (the render IS the all-gather, no
+// second pass over the tile); without it, one peer-to-peer store per rank.
+__device__ __forceinline__ void store_rgba(const RayIO& io, size_t i, float4 v) {
+    if (io.n_peers == 0) {
+        __stcs(static_cast<float4*>(io.rgba) + i, v);
+    } else if (io.rgba_multicast) {
+        float4* p = static_cast<float4*>(io.rgba_multicast) + io.peer_offset + i;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+        for (int r = 0; r < io.n_peers; ++r) static_cast<float4*>(io.rgba_peers[r])[io.peer_offset + i] = v;
+    }
+}
+
 // Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
 template <int MODEL, int LIGHT>
 __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
@@ -211,7 +226,7 @@ __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevCo
     const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
     float4 out;
     const bool disc = shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
-    __stcs(static_cast<float4*>(io.rgba) + i, out);
+    store_rgba(io, i, out);
     if (io.discard) io.discard[i] = disc ? 1 : 0;
 }
 
@@ -250,7 +265,7 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
             }
         }
     } else {
-        __stcs(static_cast<float4*>(io.rgba) + i, out);
+        store_rgba(io, i, out);
     }
     if (io.discard) io.discard[i] = disc ? 1 : 0;
 }

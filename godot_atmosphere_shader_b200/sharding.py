@@ -81,3 +81,70 @@ def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int
     for wk in works:
         wk.wait()
     return d_chunks
+
+
+# ------------------------------------------------------------------------------------------------
+# fused render + all-gather over NVLink / NVSwitch peer memory (b200atmo_render_*_peers)
+# ------------------------------------------------------------------------------------------------
+def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0):
+    """B200AtmoPeerTargets from the device addresses of one symmetric buffer as mapped in this process."""
+    from .abi import MAX_PEERS, B200AtmoPeerTargets
+
+    ptrs = [int(p) for p in buffer_ptrs]
+    if not (1 <= len(ptrs) <= MAX_PEERS):
+        raise ValueError(f"1..{MAX_PEERS} peers supported, got {len(ptrs)}")
+    if any(p == 0 for p in ptrs):
+        raise ValueError("NULL peer buffer")
+    t = B200AtmoPeerTargets()
+    for r, p in enumerate(ptrs):
+        t.d_rgba_peers[r] = p
+    t.n_peers = len(ptrs)
+    t.d_rgba_multicast = int(multicast_ptr) if multicast_ptr else None
+    t.elem_offset = int(elem_offset)
+    return t
+
+
+class SymmetricTiles:
+    """One [slots, rays_per_slot, 4] fp32 buffer per rank in symmetric memory (torch.distributed._symmetric_memory: CUDA
+    VMM allocations exchanged between the ranks' processes, plus the NVLS multicast mapping when the fabric has one).
+    Rank r's render kernels store slot r of EVERY rank's buffer directly (`targets(rank)`), so after `barrier()` each GPU
+    holds all tiles: the render is the all-gather. PyTorch is the plumbing (allocation, rendezvous, barrier) only."""
+
+    def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = True):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.slots, self.rays_per_slot = int(slots), int(rays_per_slot)
+        group = group if group is not None else dist.group.WORLD
+        self.tensor = symm_mem.empty((self.slots, self.rays_per_slot, 4), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group.group_name)
+        self.world = self.handle.world_size
+        self.rank = self.handle.rank
+        mc = getattr(self.handle, "multicast_ptr", 0) if use_multicast else 0
+        self.multicast_ptr = int(mc) if mc else None
+        self.buffer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def targets(self, slot: int):
+        return peer_targets(self.buffer_ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot)
+
+    def barrier(self):
+        """Stream-ordered inter-rank barrier on the current CUDA stream: after it, every rank's stores have landed here."""
+        self.handle.barrier()
+
+
+def render_rays_and_gather_fused(ctx, frame, d_origin_depth, d_dir_jitter, n_rays: int, tiles: "SymmetricTiles", stream=None):
+    """Weak-scaling delivery without a collective pass: this rank's rays are rendered straight into slot `rank` of every
+    rank's tile buffer; returns after the inter-rank barrier is queued (results are complete in stream order)."""
+    ctx.render_rays_peers(frame, d_origin_depth, d_dir_jitter, n_rays, tiles.targets(tiles.rank), stream=stream)
+    tiles.barrier()
+    return tiles.tensor
+
+
+def render_frame_sharded_fused(ctx, cam, d_depth, width: int, height: int, tiles: "SymmetricTiles", stream=None):
+    """Screen-tile shard of ONE frame: rank g renders rows [g*H/G, (g+1)*H/G) into every rank's full-frame buffer
+    (`tiles` built with slots=1, rays_per_slot=width*height); returns the [height, width, 4] view after the barrier."""
+    b, e = band(height, tiles.rank, tiles.world)
+    ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(0), row_begin=b, row_end=e, stream=stream)
+    tiles.barrier()
+    return tiles.tensor.view(height, width, 4)

@@ -127,6 +127,7 @@ int b200atmo_version(void);
 size_t b200atmo_sizeof_params(void);   /* ABI self-check for bindings */
 size_t b200atmo_sizeof_frame(void);
 size_t b200atmo_sizeof_camera(void);
+size_t b200atmo_sizeof_peer_targets(void);
 /* Replaces: ShaderMaterial.new() + material.shader = ... (planet_atmosphere.gd:84-108). */
 int b200atmo_create(int cuda_device, b200atmo_ctx** out);
 void b200atmo_destroy(b200atmo_ctx* ctx);
@@ -238,6 +239,28 @@ int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float
 /* HOST-buffer variant (the e2e path): H2D depth, render, D2H rgba (+discard); synchronous. */
 int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
                                int w, int h, float* h_rgba, uint8_t* h_discard);
+
+/* ---- multi-GPU: fused render + all-gather over NVLink / NVSwitch peer memory ---------------------------------- */
+/*
+ * The screen-tile shard (one process per GPU, rank g renders rows [g*H/G, (g+1)*H/G) or its own tile) ends with every
+ * rank holding every tile. Instead of rendering locally and then all-gathering, these calls make the render kernel store
+ * each finished RGBA value directly into EVERY rank's copy of a symmetric buffer (same layout on all GPUs, mapped into
+ * this process by CUDA IPC / symmetric memory, e.g. torch.distributed._symmetric_memory): with `d_rgba_multicast` (the
+ * NVLS multicast mapping of that buffer) one store per pixel is replicated by the NVSwitch; otherwise one peer-to-peer
+ * store per rank. The calls are asynchronous on `stream`; the tiles of the other ranks are complete on this GPU after an
+ * inter-rank barrier that follows the kernels (e.g. the symmetric-memory handle's barrier). No discard mask.
+ */
+#define B200ATMO_MAX_PEERS 8
+typedef struct B200AtmoPeerTargets {
+    void* d_rgba_peers[B200ATMO_MAX_PEERS]; /* the symmetric buffer as mapped here, one pointer per rank (own rank included) */
+    int32_t n_peers;                        /* 1..B200ATMO_MAX_PEERS */
+    void* d_rgba_multicast;                 /* NVLS multicast mapping of the same buffer, or NULL */
+    uint64_t elem_offset;                   /* float4 elements added to the pixel / ray index (this rank's slot) */
+} B200AtmoPeerTargets;
+int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                int row_begin, int row_end, const B200AtmoPeerTargets* targets, void* stream);
+int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth,
+                               const float* d_dir_jitter, size_t n_rays, const B200AtmoPeerTargets* targets, void* stream);
 
 /*
  * Pipelined form of b200atmo_render_frame_host for a stream of frames (one per _process tick, or the tiles of an

@@ -27,6 +27,7 @@ def test_struct_sizes_match():
     assert lib.b200atmo_sizeof_params() == C.sizeof(abi.B200AtmoParams)
     assert lib.b200atmo_sizeof_frame() == C.sizeof(abi.B200AtmoFrame)
     assert lib.b200atmo_sizeof_camera() == C.sizeof(abi.B200AtmoCamera)
+    assert lib.b200atmo_sizeof_peer_targets() == C.sizeof(abi.B200AtmoPeerTargets)
 
 
 def test_default_params_match_shader_defaults():

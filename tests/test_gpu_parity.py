@@ -303,6 +303,42 @@ def test_pipelined_host_frames_equal_the_synchronous_call(cuda_ctx_factory):
     assert np.array_equal(rgba.numpy().view(np.uint32), want.view(np.uint32))
 
 
+def test_peer_store_paths_on_one_gpu(cuda_ctx_factory):
+    """b200atmo_render_frame_peers / b200atmo_render_rays_peers with the peer table pointing at buffers of THIS GPU
+    (the P2P-store path; the NVLS multicast path needs 2 GPUs: tests/test_multigpu_fused.py): every target buffer gets
+    the bits of the plain call, only rows [row_begin,row_end) / slot elem_offset are written."""
+    torch = _torch()
+    from godot_atmosphere_shader_b200 import sharding
+    from godot_atmosphere_shader_b200.context import B200AtmoError
+    ctx = cuda_ctx_factory()
+    w, h = 192, 108
+    p = scenes.demo_params()
+    _setup(ctx, p, VARIANTS["clouds"])
+    cam = scenes.camera_a(w, h)
+    depth = scenes.synth_depth(cam, p, w, h)
+    d_depth = torch.from_numpy(depth).cuda()
+    want = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, want, None)
+    bufs = [torch.full((3, h * w, 4), -7.0, dtype=torch.float32, device="cuda") for _ in range(3)]
+    t = sharding.peer_targets([b.data_ptr() for b in bufs], elem_offset=1 * h * w)       # slot 1 of [3, n, 4]
+    ctx.render_frame_peers(cam, d_depth, w, h, t, row_begin=0, row_end=h // 3)
+    ctx.render_frame_peers(cam, d_depth, w, h, t, row_begin=h // 3, row_end=h)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[1], want) and bool((b[0] == -7.0).all()) and bool((b[2] == -7.0).all())
+    d_od = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    d_dj = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj)
+    t2 = sharding.peer_targets([bufs[0].data_ptr(), bufs[2].data_ptr()], elem_offset=2 * h * w)
+    ctx.render_rays_peers(fr, d_od, d_dj, h * w, t2)
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0][2], want) and torch.equal(bufs[2][2], want) and bool((bufs[1][2] == -7.0).all())
+    bad = sharding.peer_targets([bufs[0].data_ptr()])
+    bad.n_peers = 9
+    with pytest.raises(B200AtmoError):
+        ctx.render_rays_peers(fr, d_od, d_dj, h * w, bad)
+
+
 def test_full_size_properties(cuda_ctx_factory):
     """BASELINE config[1] size (1920x1080, N=32): size-independent properties instead of a full oracle run."""
     torch = _torch()

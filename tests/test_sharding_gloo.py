@@ -73,3 +73,19 @@ def test_gloo_band_gather(tmp_path, world, h):
     for r in range(world):
         got = np.load(tmp_path / f"full_{r}.npy")
         assert np.array_equal(got, want), f"rank {r}: gathered frame differs from the single-process frame"
+
+
+def test_peer_targets_validation():
+    """Host side of the fused render + all-gather: the B200AtmoPeerTargets block built from symmetric-memory addresses."""
+    from godot_atmosphere_shader_b200 import abi, sharding
+    t = sharding.peer_targets([0x1000, 0x2000, 0x3000], multicast_ptr=0x9000, elem_offset=7)
+    assert t.n_peers == 3 and [t.d_rgba_peers[r] for r in range(3)] == [0x1000, 0x2000, 0x3000]
+    assert t.d_rgba_peers[3] is None and t.d_rgba_multicast == 0x9000 and t.elem_offset == 7
+    assert sharding.peer_targets([0x1000]).d_rgba_multicast is None
+    import pytest
+    with pytest.raises(ValueError):
+        sharding.peer_targets([])
+    with pytest.raises(ValueError):
+        sharding.peer_targets([0x1000] * (abi.MAX_PEERS + 1))
+    with pytest.raises(ValueError):
+        sharding.peer_targets([0x1000, 0])

@@ -349,6 +349,27 @@ def run_ours(a, rank, world, local_rank):
         dist.all_reduce(g, op=dist.ReduceOp.MAX)
         gather = {"ms_per_step": float(g.item()), "value": world * ray_steps / (float(g.item()) * 1e-3), "unit": UNIT,
                   "bytes_gathered_per_gpu": world * n_rays * 16, "collective": "ncclAllGather (torch.distributed)"}
+        # fused: the render kernel stores every finished RGBA value into all ranks' symmetric buffers over NVLink
+        # (NVLS multicast when the fabric offers it) -- the render IS the all-gather, no collective pass
+        from godot_atmosphere_shader_b200.sharding import SymmetricTiles, render_rays_and_gather_fused
+        fused = {}
+        for label, use_mc in (("multicast", True), ("p2p", False)):
+            try:
+                tiles = SymmetricTiles(world, n_rays, dev, use_multicast=use_mc)
+                if use_mc and not tiles.multicast_ptr:
+                    fused[label] = {"unavailable": "no NVLS multicast mapping on this fabric"}
+                    continue
+                fms2, _ = timed_loop(lambda: render_rays_and_gather_fused(ctx, fr, d_od, d_dj, n_rays, tiles, stream=stream),
+                                     max(10, a.steps // 4), 3)
+                fz = torch.tensor([fms2 / max(10, a.steps // 4)], dtype=torch.float64, device=dev)
+                dist.all_reduce(fz, op=dist.ReduceOp.MAX)
+                ok = bool(torch.equal(tiles.tensor.view(world * n_rays, 4), gathered))
+                fused[label] = {"ms_per_step": float(fz.item()), "value": world * ray_steps / (float(fz.item()) * 1e-3),
+                                "tiles_match_nccl": ok}
+                del tiles
+            except Exception as exc:  # symmetric memory unavailable (no P2P / driver support): report, do not fail the bench
+                fused[label] = {"unavailable": repr(exc)[:200]}
+        gather["fused"] = dict(fused, api="b200atmo_render_rays_peers + symmetric-memory barrier (timed incl. the barrier)")
         # chunked + overlapped delivery through the frame API (sharding.render_tile_and_gather_overlapped)
         from godot_atmosphere_shader_b200.sharding import render_tile_and_gather_overlapped
         mine = torch.empty((h, w, 4), dtype=torch.float32, device=dev)

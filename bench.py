@@ -252,6 +252,32 @@ def load_ncu_facts(a):
         return {}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank's host thread on the CPUs of its GPU's NUMA node (so its pinned buffers are allocated there and the
+    PCIe copies do not cross the socket interconnect). Best effort: returns the node or None, never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:   # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        usable = cpus & os.sched_getaffinity(0)
+        if usable:
+            os.sched_setaffinity(0, usable)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -259,6 +285,7 @@ def run_ours(a, rank, world, local_rank):
     from godot_atmosphere_shader_b200 import context
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback for the product path"
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     w, h, N = a.width, a.height, a.scatter_steps
@@ -462,7 +489,8 @@ def run_ours(a, rank, world, local_rank):
                 "d2h_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_OUT, "ms_per_step": e2e_s * 1e3,
                 "api": "b200atmo_render_frame_host_submit + b200atmo_frame_wait (pinned host depth in, RGBA out; 2 pipeline "
                        "slots: frame k's D2H overlaps frame k+1's H2D + kernel)",
-                "timer": "host perf_counter around the whole loop incl. the final waits", "matches_device_path": e2e_ok,
+                "timer": "host perf_counter around the whole loop incl. the final waits, max over ranks", "matches_device_path": e2e_ok,
+                "host_numa_node_rank0": numa_node,
                 "synchronous": {"value": world * ray_steps / e2e_sync_s, "ms_per_step": e2e_sync_s * 1e3,
                                 "api": "b200atmo_render_frame_host (one frame at a time, 4 row bands over 2 streams)"}},
         "e2e_composite_rgba16f": {"ms_per_step": comp_s * 1e3, "value": ray_steps / comp_s, "unit": UNIT,

@@ -110,7 +110,7 @@ class SymmetricTiles:
     Rank r's render kernels store slot r of EVERY rank's buffer directly (`targets(rank)`), so after `barrier()` each GPU
     holds all tiles: the render is the all-gather. PyTorch is the plumbing (allocation, rendezvous, barrier) only."""
 
-    def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = True):
+    def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem

@@ -653,7 +653,7 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     return B200ATMO_OK;
 }
 
-static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIO& io, const char* who) {
+static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPeers& io, const char* who) {
     if (!t) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL targets");
     if (t->n_peers < 1 || t->n_peers > B200ATMO_MAX_PEERS) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": n_peers out of range");
     for (int r = 0; r < t->n_peers; ++r) {
@@ -671,7 +671,7 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
     if (!ctx || !cam || !d_depth) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_peers: NULL argument");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    RayIO io{};
+    RayIOPeers io{};
     int rc = peers_to_io(ctx, targets, io, "b200atmo_render_frame_peers");
     if (rc != B200ATMO_OK) return rc;
     DevConsts c;
@@ -680,7 +680,7 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
     if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
     io.depth = d_depth;
     io.n = size_t(w) * h;
-    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    CU_TRY(ctx, launch_render_frame_peers(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
 }
@@ -688,7 +688,7 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
                                size_t n_rays, const B200AtmoPeerTargets* targets, void* stream) {
     if (!ctx || !frame) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_peers: NULL ctx/frame");
-    RayIO io{};
+    RayIOPeers io{};
     int rc = peers_to_io(ctx, targets, io, "b200atmo_render_rays_peers");
     if (rc != B200ATMO_OK) return rc;
     if (n_rays == 0) return B200ATMO_OK;
@@ -703,7 +703,7 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
     io.origin_depth = d_origin_depth;
     io.dir_jitter = d_dir_jitter;
     io.n = n_rays;
-    CU_TRY(ctx, launch_render_rays(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    CU_TRY(ctx, launch_render_rays_peers(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
 }

@@ -71,16 +71,19 @@ struct RayIO {
     void* rgba;                // float4[...] out
     void* color_inout;         // frame colour buffer to blend into (frame kernel; then rgba may be null): float4[w*h] or half4[w*h]
     int color_format;          // B200ATMO_COLOR_RGBA32F / B200ATMO_COLOR_RGBA16F
-    // fused render + all-gather (b200atmo_render_*_peers): the result goes to the same symmetric buffer on every GPU
-    // instead of `rgba`: one multimem store when the NVLS multicast mapping is given, else one P2P store per peer
-    void* rgba_peers[B200ATMO_MAX_PEERS];
-    void* rgba_multicast;
-    int n_peers;               // 0 = plain local store to `rgba`
-    size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
     uint8_t* discard;          // nullable
     void* out_origin_depth;    // make_rays only
     void* out_dir_jitter;
     size_t n;
+};
+// fused render + all-gather (b200atmo_render_*_peers): the result goes to the same symmetric buffer on every GPU instead
+// of `rgba`: one multimem store when the NVLS multicast mapping is given, else one P2P store per peer. A separate
+// parameter type, so the single-GPU kernels keep exactly the code (and parameter layout) they have without this path.
+struct RayIOPeers : RayIO {
+    void* rgba_peers[B200ATMO_MAX_PEERS];
+    void* rgba_multicast;
+    int n_peers;
+    size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
 };
 
 #ifdef __CUDACC__
@@ -90,6 +93,8 @@ cudaError_t launch_cube_pad(const uint8_t* d_faces, int res, uint8_t* d_padded, 
 cudaError_t launch_shape_pad(const uint8_t* d_src, int nx, int ny, int nz, float* d_dst, float4* d_cells, cudaStream_t s);
 cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], int res, uint8_t* d_faces, cudaStream_t s);
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
+cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s);
+cudaError_t launch_render_frame_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
 #endif

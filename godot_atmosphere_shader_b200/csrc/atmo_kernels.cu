@@ -205,10 +205,11 @@ constexpr int kBlock = B200ATMO_BLOCK;
 // Result store. Multi-GPU shards write straight into every rank's copy of a symmetric buffer over NVLink: with the NVLS
 // multicast mapping one 16-byte store is replicated by the NVSwitch to all GPUs (the render IS the all-gather, no
 // second pass over the tile); without it, one peer-to-peer store per rank.
-__device__ __forceinline__ void store_rgba(const RayIO& io, size_t i, float4 v) {
-    if (io.n_peers == 0) {
-        __stcs(static_cast<float4*>(io.rgba) + i, v);
-    } else if (io.rgba_multicast) {
+// Overloaded on the parameter type (RayIOPeers only for the *_peers kernels): the single-GPU kernels compile to
+// exactly the code they have without this path.
+__device__ __forceinline__ void store_rgba(const RayIO& io, size_t i, float4 v) { __stcs(static_cast<float4*>(io.rgba) + i, v); }
+__device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float4 v) {
+    if (io.rgba_multicast) {
         float4* p = static_cast<float4*>(io.rgba_multicast) + io.peer_offset + i;
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                      : "memory");
@@ -218,8 +219,8 @@ __device__ __forceinline__ void store_rgba(const RayIO& io, size_t i, float4 v) 
 }
 
 // Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
-template <int MODEL, int LIGHT>
-__global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+template <int MODEL, int LIGHT, class IO>
+__global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const size_t i = blockIdx.x * size_t(kBlock) + threadIdx.x;
     if (i >= io.n) return;
     const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
@@ -232,8 +233,8 @@ __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevCo
 
 // Frame: a warp covers an 8x4 pixel tile (coherent LUT / texture footprints, full 128 B store
 // segments per tile row), a block of 4 warps a 16x8 tile.
-template <int MODEL, int LIGHT>
-__global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const RayIO io) {
+template <int MODEL, int LIGHT, class IO>
+__global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = c.row_begin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -282,32 +283,43 @@ __global__ void __launch_bounds__(kBlock) make_rays_kernel(const __grid_constant
     static_cast<float4*>(io.out_dir_jitter)[i] = make_float4(d.x, d.y, d.z, jitter);
 }
 
-#define B200ATMO_DISPATCH(KERNEL, GRID, ...)                                                               \
-    do {                                                                                                   \
-        if (scatter_model == B200ATMO_SCATTER_V1) {                                                         \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);       \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<1, 2><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                         \
-        } else {                                                                                           \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);       \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<0, 2><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                         \
-        }                                                                                                  \
+#define B200ATMO_DISPATCH(KERNEL, IO, GRID, ...)                                                              \
+    do {                                                                                                     \
+        if (scatter_model == B200ATMO_SCATTER_V1) {                                                           \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);     \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<1, 2, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                       \
+        } else {                                                                                             \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);     \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<0, 2, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                       \
+        }                                                                                                    \
     } while (0)
 
-cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+template <class IO> static cudaError_t launch_rays_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     if (io.n == 0) return cudaSuccess;
     const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
-    B200ATMO_DISPATCH(render_rays_kernel, grid, c, io);
+    B200ATMO_DISPATCH(render_rays_kernel, IO, grid, c, io);
     return cudaGetLastError();
 }
-
-cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+template <class IO> static cudaError_t launch_frame_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     const int rows = c.row_end - c.row_begin;
     if (rows <= 0 || c.fw <= 0) return cudaSuccess;
     const dim3 grid((c.fw + 15) / 16, (rows + 7) / 8);
-    B200ATMO_DISPATCH(render_frame_kernel, grid, c, io);
+    B200ATMO_DISPATCH(render_frame_kernel, IO, grid, c, io);
     return cudaGetLastError();
+}
+cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+    return launch_rays_t(c, io, scatter_model, light_mode, s);
+}
+cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s) {
+    return launch_rays_t(c, io, scatter_model, light_mode, s);
+}
+cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+    return launch_frame_t(c, io, scatter_model, light_mode, s);
+}
+cudaError_t launch_render_frame_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s) {
+    return launch_frame_t(c, io, scatter_model, light_mode, s);
 }
 
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s) {

@@ -167,37 +167,51 @@ def usable_cpus():
 
 
 def cpu_frame_runner(a, budget_s_per_step):
-    """Returns (run, info): run() renders one bounded sample with the oracle and returns (seconds, ray_steps)."""
+    """Returns (run, info): run() renders one bounded sample on the host cores and returns (seconds, ray_steps).
+
+    kind "reference": oracle/_ref — the reference's own GDShader sources compiled as C++ (oracle/ref/build_ref.py; built
+    where /root/reference exists, the .so travels with the repo), its fragment() run per pixel of every `stride`-th row.
+    kind "port" (only if that library is missing): the hand-written scalar C++ oracle on the same rows."""
     from oracle import pyoracle as O
+    from oracle import pyref as R
     p, cam, depth, tex = build_scene(a)
     otex = O.Textures(lut=O.bake_lut(p), shape=tex.get("shape"), cube_faces=tex.get("cube"), blue_noise=tex["bn"])
     var = O.variant(a.scatter_steps, a.cloud_steps, a.light)
     threads, cpu_info = usable_cpus()
     w, h = a.width, a.height
-    od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
+    use_ref = R.available()
+    if use_ref:
+        def render(stride):
+            t0 = time.perf_counter()
+            _, disc = R.render_frame(p, var, cam, otex, depth, w, h, threads=threads, row_stride=stride)
+            dt = time.perf_counter() - t0
+            return dt, int((disc[::stride] == 0).sum()) * a.scatter_steps
+    else:
+        od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
 
-    def render(sel_od, sel_dj):
-        t0 = time.perf_counter()
-        _, disc = O.render_rays(p, var, fr, otex, sel_od, sel_dj, threads=threads)
-        dt = time.perf_counter() - t0
-        return dt, int((disc == 0).sum()) * a.scatter_steps
+        def render(stride):
+            rows = np.arange(0, h, stride)
+            idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
+            s_od, s_dj = np.ascontiguousarray(od[idx]), np.ascontiguousarray(dj[idx])
+            t0 = time.perf_counter()
+            _, disc = O.render_rays(p, var, fr, otex, s_od, s_dj, threads=threads)
+            dt = time.perf_counter() - t0
+            return dt, int((disc == 0).sum()) * a.scatter_steps
 
     # calibrate on 1/16 of the rows, then pick a row stride that keeps one step under the budget
-    rows = np.arange(0, h, 16)
-    idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
-    dt, _ = render(od[idx], dj[idx])
-    dt, _ = render(od[idx], dj[idx])
+    render(16)
+    dt, _ = render(16)
     full_est = dt * 16
     stride = 1
     while full_est / stride > budget_s_per_step and stride < h:
         stride *= 2
-    rows = np.arange(0, h, stride)
-    idx = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
-    s_od, s_dj = np.ascontiguousarray(od[idx]), np.ascontiguousarray(dj[idx])
-    info = {"cores": threads, "host": cpu_info, "kind": "port",
-            "sample": (f"full {w}x{h} frame" if stride == 1 else f"every {stride}th row of the {w}x{h} frame ({len(rows)} rows)")
-                      + f", {a.scatter_steps} steps, scalar C++ oracle -O2 no-FMA, {threads} std::thread workers"}
-    return (lambda: render(s_od, s_dj)), info
+    n_rows = len(range(0, h, stride))
+    what = ("the reference's GDShader sources compiled as C++ (oracle/_ref), fragment() per pixel" if use_ref
+            else "scalar C++ oracle port -O2 no-FMA (oracle/_ref not built)")
+    info = {"cores": threads, "host": cpu_info, "kind": "reference" if use_ref else "port",
+            "sample": (f"full {w}x{h} frame" if stride == 1 else f"every {stride}th row of the {w}x{h} frame ({n_rows} rows)")
+                      + f", {a.scatter_steps} steps, {what}, {threads} std::thread workers"}
+    return (lambda: render(stride)), info
 
 
 def run_reference(a, rank, world):
@@ -222,7 +236,7 @@ def run_reference(a, rank, world):
         "cpu_baseline": dict(info, value=value, unit=UNIT),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference ships no CPU implementation (GDShader only); this arm is the scalar C++ oracle port",
+        "note": "the reference ships no CPU implementation (GDShader only); this arm runs its shader sources compiled as C++ on the host cores (kind reference), or the oracle port if that library is missing",
     }
     emit(line)
 

@@ -6,11 +6,15 @@
 // cpu_baseline / --impl reference legs may load this; the product (godot_atmosphere_shader_b200/)
 // never does.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or CPU implementation, and its only
-// executable form is GDShader text that needs the Godot >=4.3 engine + a Vulkan GPU (absent here).
-// This file is therefore pinned only by (1) known-answer tests derived by hand from the shader
-// source (tests/test_oracle_kat.py), (2) its own fp64 instantiation (same template, T=double), and
-// (3) self-generated golden vectors (tests/golden/, generator committed).
+// PARITY PIN: the reference ships no tests, golden vectors or CPU implementation, and Godot (the only thing that
+// runs GDShader) is absent here. The pin is the reference's OWN SOURCE TEXT: oracle/ref/build_ref.py compiles the
+// shader files where they lie under /root/reference as C++ (a purely syntactic rewrite + a header of GLSL types and
+// built-ins) into oracle/_ref/libatmo_ref.so, and tests/test_reference_pin.py requires this file (T=float) to equal
+// it BIT FOR BIT — LUT, discard masks, fp32 RGBA — for all 7 shipped entry shaders, the BASELINE scale-ups, corner
+// cameras and random scenes; a mutation test shows the comparison has teeth. What stays unpinned is what the
+// reference leaves to the engine / GPU (the rounding of GLSL built-ins, texture filtering): defined below, used by
+// both sides. Further pins: known-answer tests derived by hand from the shader source (tests/test_oracle_kat.py), the
+// fp64 instantiation (same template, T=double), self-generated golden vectors (tests/golden/, generator committed).
 //
 // Everything is templated on the scalar T: T=float is THE oracle (fp32, the shader's precision;
 // build with -ffp-contract=off so no FMA contraction happens), T=double bounds its rounding error.

@@ -1,7 +1,8 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY. ctypes front end of oracle/liboracle.so (atmo_oracle.cpp).
 
 May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs only. The product package never imports this module. PARITY UNPINNED — see atmo_oracle.hpp.
+legs only. The product package never imports this module. Pinned bit for bit to the reference's own shader sources compiled as C++ (oracle/pyref.py,
+tests/test_reference_pin.py) — see atmo_oracle.hpp.
 """
 import ctypes as C
 import os

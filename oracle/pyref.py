@@ -69,7 +69,7 @@ def bake_lut(params: B200AtmoParams) -> np.ndarray:
 
 
 def render_frame(params, var: OracleVariant, cam: B200AtmoCamera, tex: Textures, depth, w, h, row_begin=0, row_end=None,
-                 threads=1, shader: str = None):
+                 threads=1, shader: str = None, row_stride=1):
     """One draw with the compiled entry shader `shader` (default: the shipped shader whose feature #defines match `var`)."""
     assert not (cam.clip_box_size > 0.0), "the MODE_FAR proxy mesh is rasteriser behaviour, not shader code"
     row_end = h if row_end is None else row_end
@@ -78,7 +78,7 @@ def render_frame(params, var: OracleVariant, cam: B200AtmoCamera, tex: Textures,
     disc = np.zeros((h, w), dtype=np.uint8)
     ts = tex.struct()
     rc = lib().ref_render_frame_f32(shader.encode() if shader else None, C.byref(params), C.byref(var), C.byref(cam), C.byref(ts),
-                                    _ptr(dep), C.c_int(w), C.c_int(h), C.c_int(row_begin), C.c_int(row_end), _ptr(rgba), _ptr(disc),
+                                    _ptr(dep), C.c_int(w), C.c_int(h), C.c_int(row_begin), C.c_int(row_end), C.c_int(row_stride), _ptr(rgba), _ptr(disc),
                                     C.c_int(threads))
     if rc != 0:
         raise ValueError(f"no compiled reference shader for variant {tuple(getattr(var, f) for f, _ in var._fields_)} / {shader}")

@@ -13,7 +13,7 @@ struct RefVariant {
 #define REF_DECL(name)                                                                                                        \
     extern "C" void ref_##name##_defines(int out[4]);                                                                         \
     extern "C" void ref_##name##_render_frame_f32(const B200AtmoParams*, const RefVariant*, const B200AtmoCamera*, const RefTextures*, \
-                                                  const float*, int, int, int, int, float*, uint8_t*, int);
+                                                  const float*, int, int, int, int, int, float*, uint8_t*, int);
 REF_DECL(planet_atmosphere_no_clouds)
 REF_DECL(planet_atmosphere_clouds)
 REF_DECL(planet_atmosphere_clouds_high)
@@ -25,7 +25,7 @@ REF_DECL(planet_atmosphere_v1_clouds_high)
 namespace {
 typedef void (*DefinesFn)(int[4]);
 typedef void (*RenderFn)(const B200AtmoParams*, const RefVariant*, const B200AtmoCamera*, const RefTextures*, const float*, int, int,
-                         int, int, float*, uint8_t*, int);
+                         int, int, int, float*, uint8_t*, int);
 struct Entry {
     const char* name;
     DefinesFn defines;
@@ -65,8 +65,8 @@ int ref_entry_defines(int i, int out[4]) {
 // Renders with entry shader `name`, or (name == NULL) with the first shipped shader whose feature #defines match the
 // variant (step counts are runtime values in the compiled shaders). Returns 0, or -1 if there is no such shader.
 int ref_render_frame_f32(const char* name, const B200AtmoParams* p, const RefVariant* v, const B200AtmoCamera* cam,
-                         const RefTextures* tex, const float* depth, int w, int h, int row_begin, int row_end, float* rgba,
-                         uint8_t* discard, int threads) {
+                         const RefTextures* tex, const float* depth, int w, int h, int row_begin, int row_end, int row_stride,
+                         float* rgba, uint8_t* discard, int threads) {
     for (const Entry& e : g_entries) {
         if (name) {
             if (std::strcmp(name, e.name) != 0) continue;
@@ -75,7 +75,7 @@ int ref_render_frame_f32(const char* name, const B200AtmoParams* p, const RefVar
             const bool clouds = v->light_mode != B200ATMO_LIGHT_NONE, rm = v->light_mode == B200ATMO_LIGHT_RAYMARCHED;
             if (lite != (e.lite != 0) || clouds != (e.cloud_steps != 0) || (clouds && rm != (e.rm != 0))) continue;
         }
-        e.render(p, v, cam, tex, depth, w, h, row_begin, row_end, rgba, discard, threads);
+        e.render(p, v, cam, tex, depth, w, h, row_begin, row_end, row_stride, rgba, discard, threads);
         return 0;
     }
     return -1;

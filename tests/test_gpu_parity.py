@@ -339,6 +339,39 @@ def test_peer_store_paths_on_one_gpu(cuda_ctx_factory):
         ctx.render_rays_peers(fr, d_od, d_dj, h * w, bad)
 
 
+@pytest.mark.parametrize("shader", ["planet_atmosphere_no_clouds", "planet_atmosphere_clouds", "planet_atmosphere_clouds_high",
+                                    "planet_atmosphere_clouds_high_rm", "planet_atmosphere_v1_no_clouds", "planet_atmosphere_v1_clouds",
+                                    "planet_atmosphere_v1_clouds_high"])
+def test_cuda_path_vs_the_compiled_reference_shaders(cuda_ctx_factory, shader):
+    """The CUDA path against oracle/_ref — the reference's OWN GDShader sources compiled as C++ (oracle/ref/build_ref.py),
+    not the hand-written restatement: LUT and discard mask bit-exact, RGBA within the north_star tolerance
+    (1e-4 relative per channel + 2e-6), for every shipped entry shader run by name with its own #defines."""
+    from godot_atmosphere_shader_b200.planet_atmosphere import SHADER_VARIANTS
+    from oracle import pyref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libatmo_ref.so was not built (needs /root/reference at build time)")
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    model, ns, nc, light = SHADER_VARIANTS[shader]
+    assert R.entry_shaders()[shader][1:3] == (ns, nc)
+    p = scenes.demo_params()
+    if model == abi.SCATTER_V1:
+        p.density = 0.02
+    tex = _setup(ctx, p, (model, ns, nc, light))
+    if model == abi.SCATTER_V2:
+        assert np.array_equal(ctx.download_lut().view(np.uint32), R.bake_lut(p).view(np.uint32)), "LUT differs from optical_depth.gdshader"
+    w, h = (128, 72) if light == abi.LIGHT_RAYMARCHED else (224, 126)
+    for cam in (scenes.camera_a(w, h), scenes.camera_b(w, h, p)):
+        depth = scenes.synth_depth(cam, p, w, h)
+        d_rgba = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+        d_disc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+        ctx.render_frame(cam, torch.from_numpy(depth).cuda(), w, h, d_rgba, d_disc)
+        torch.cuda.synchronize()
+        ref, rdisc = R.render_frame(p, O.variant(ns, nc, light, model), cam, tex, depth, w, h, threads=0, shader=shader)
+        assert np.array_equal(d_disc.cpu().numpy(), rdisc)
+        Hh.assert_rgba_close(d_rgba.cpu().numpy(), ref, what=f"{shader} vs compiled reference")
+
+
 def test_full_size_properties(cuda_ctx_factory):
     """BASELINE config[1] size (1920x1080, N=32): size-independent properties instead of a full oracle run."""
     torch = _torch()

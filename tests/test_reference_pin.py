@@ -176,7 +176,7 @@ def test_the_pin_has_teeth(tmp_path):
     disc = np.zeros((h, w), np.uint8)
     ts = tex.struct()
     assert mlib.ref_render_frame_f32(None, C.byref(p), C.byref(var), C.byref(cam), C.byref(ts), O._ptr(np.ascontiguousarray(depth, np.float32)),
-                                     w, h, 0, h, O._ptr(rgba), O._ptr(disc), 1) == 0
+                                     w, h, 0, h, 1, O._ptr(rgba), O._ptr(disc), 1) == 0
     got, _ = O.render_frame(p, var, cam, tex, depth, w, h)
     assert np.array_equal(_bits(got[..., :3]), _bits(rgba[..., :3]))          # colour untouched by the mutation
     assert (_bits(got[..., 3]) != _bits(rgba[..., 3])).mean() > 0.9            # alpha differs wherever jitter > 0

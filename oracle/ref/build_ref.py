@@ -20,10 +20,11 @@ The rewrite touches syntax only (no expression is reordered, no constant changed
     (so the BASELINE scale-ups 32 / 128 run through the same code); `#ifdef DOUBLE_PRECISION ... #endif` -> a runtime `if`
   * one C++-only name clash: cloud_funcs.gdshaderinc:39 declares a local `height_curve` initialised by a call to the
     function `height_curve` (legal GLSL scoping, ill-formed C++): the local is renamed
-Generated sources and the library go to oracle/_ref/ only (git-ignored; the .so travels to the GPU box, where
-/root/reference does not exist). Nothing of the reference is copied into the tracked tree.
+The generated C++ lives in a temporary directory during the build and is deleted; only libatmo_ref.so lands in
+oracle/_ref/ (git-ignored; it travels to the GPU box, where /root/reference does not exist). Nothing of the reference is
+copied into the repo tree.
 
-usage: python oracle/ref/build_ref.py [--reference /root/reference] [--keep-going]
+usage: python oracle/ref/build_ref.py [--reference /root/reference] [--keep-sources /tmp/dir]
 """
 import argparse
 import os
@@ -126,51 +127,61 @@ GLSL_USING
     return src, subs
 
 
-def build(reference="/root/reference", verbose=True, out_dir=None):
+def build(reference="/root/reference", verbose=True, out_dir=None, keep_sources=None):
+    """Generates the C++ sources in a temporary directory, compiles them and leaves ONLY libatmo_ref.so in `out_dir`
+    (default oracle/_ref): the rewritten shader text is a derived copy of the reference and is not kept in the repo tree
+    (`keep_sources=<dir>` keeps it there for debugging)."""
+    import shutil
+    import tempfile
     if not os.path.isdir(os.path.join(reference, SHADERS)):
         raise FileNotFoundError(f"{reference}/{SHADERS} not found: the reference tree is needed to build oracle/_ref")
     out_root = out_dir or OUT
     os.makedirs(out_root, exist_ok=True)
-    sources = []
-    for name in ENTRY_SHADERS:
-        src, subs = gen_entry(reference, name)
-        p = os.path.join(out_root, f"gen_{name}.cpp")
+    work = keep_sources or tempfile.mkdtemp(prefix="b200atmo_ref_")
+    os.makedirs(work, exist_ok=True)
+    try:
+        sources = []
+        for name in ENTRY_SHADERS:
+            src, subs = gen_entry(reference, name)
+            p = os.path.join(work, f"gen_{name}.cpp")
+            open(p, "w").write(src)
+            sources.append(p)
+            if verbose:
+                print(f"  {name}: " + ", ".join(f"{k} x{v}" for k, v in subs.items() if v))
+        src, subs = gen_bake(reference)
+        p = os.path.join(work, "gen_optical_depth.cpp")
         open(p, "w").write(src)
         sources.append(p)
+        sources.append(os.path.join(HERE, "ref_dispatch.cpp"))
+        lib = os.path.join(out_root, "libatmo_ref.so")
+        cxx = os.environ.get("CXX", "g++")
+        flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-Wno-unused-variable",
+                 "-Wno-unused-function", "-Wno-unused-but-set-variable", "-I" + HERE]
+        objs, procs = [], []
+        for s in sources:
+            o = os.path.join(work, os.path.basename(s)[:-4] + ".o")
+            objs.append(o)
+            procs.append((s, subprocess.Popen([cxx] + flags + ["-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        failed = False
+        for s, pr in procs:
+            out, _ = pr.communicate()
+            if pr.returncode != 0:
+                failed = True
+                sys.stderr.write(f"--- {s}\n{out[-6000:]}\n")
+        if failed:
+            raise RuntimeError("oracle/_ref: compiling the rewritten reference shaders failed")
+        subprocess.check_call([cxx, "-shared", "-pthread", "-o", lib] + objs)
         if verbose:
-            print(f"  {name}: " + ", ".join(f"{k} x{v}" for k, v in subs.items() if v))
-    src, subs = gen_bake(reference)
-    p = os.path.join(out_root, "gen_optical_depth.cpp")
-    open(p, "w").write(src)
-    sources.append(p)
-    sources.append(os.path.join(HERE, "ref_dispatch.cpp"))
-    lib = os.path.join(out_root, "libatmo_ref.so")
-    cxx = os.environ.get("CXX", "g++")
-    flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-Wno-unused-variable",
-             "-Wno-unused-function", "-Wno-unused-but-set-variable", "-I" + HERE, "-shared"]
-    objs = []
-    procs = []
-    for s in sources:
-        o = os.path.join(out_root, os.path.basename(s)[:-4] + ".o")
-        objs.append(o)
-        procs.append((s, subprocess.Popen([cxx] + [f for f in flags if f != "-shared"] + ["-c", s, "-o", o],
-                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    failed = False
-    for s, pr in procs:
-        out, _ = pr.communicate()
-        if pr.returncode != 0:
-            failed = True
-            sys.stderr.write(f"--- {s}\n{out[-6000:]}\n")
-    if failed:
-        raise RuntimeError("oracle/_ref: compiling the rewritten reference shaders failed")
-    subprocess.check_call([cxx, "-shared", "-pthread", "-o", lib] + objs)
-    if verbose:
-        print(f"built {lib}")
-    return lib
+            print(f"built {lib}")
+        return lib
+    finally:
+        if not keep_sources:
+            shutil.rmtree(work, ignore_errors=True)
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default=os.environ.get("B200ATMO_REFERENCE", "/root/reference"))
+    ap.add_argument("--keep-sources", default=None, help="directory to keep the generated C++ in (debugging; keep it outside the repo)")
     a = ap.parse_args()
-    build(a.reference)
+    build(a.reference, keep_sources=a.keep_sources)

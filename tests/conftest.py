@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once (nvcc cross-compiles without a GPU)
+    pkg = os.path.join(ROOT, "godot_atmosphere_shader_b200")
+    if not (os.path.exists(os.path.join(pkg, "libb200atmo.so")) and os.path.exists(os.path.join(pkg, "libb200atmo_node.so"))):
+        import subprocess
+        subprocess.check_call(["bash", os.path.join(pkg, "csrc", "build.sh")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")

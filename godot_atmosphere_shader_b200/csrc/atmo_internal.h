@@ -83,6 +83,7 @@ struct RayIOPeers : RayIO {
     void* rgba_peers[B200ATMO_MAX_PEERS];
     void* rgba_multicast;
     int n_peers;
+    int first_peer;            // store loop starts here and wraps (ranks stagger their destinations)
     size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
 };
 

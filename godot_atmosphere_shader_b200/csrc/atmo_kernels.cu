@@ -214,7 +214,11 @@ __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                      : "memory");
     } else {
-        for (int r = 0; r < io.n_peers; ++r) static_cast<float4*>(io.rgba_peers[r])[io.peer_offset + i] = v;
+        int r = io.first_peer;
+        for (int k = 0; k < io.n_peers; ++k) {
+            static_cast<float4*>(io.rgba_peers[r])[io.peer_offset + i] = v;
+            r = (r + 1 == io.n_peers) ? 0 : r + 1;
+        }
     }
 }
 

@@ -256,6 +256,8 @@ typedef struct B200AtmoPeerTargets {
     int32_t n_peers;                        /* 1..B200ATMO_MAX_PEERS */
     void* d_rgba_multicast;                 /* NVLS multicast mapping of the same buffer, or NULL */
     uint64_t elem_offset;                   /* float4 elements added to the pixel / ray index (this rank's slot) */
+    int32_t first_peer;                     /* P2P path: index the store loop starts at (wraps around). Pass (rank + 1) % n_peers so
+                                               that at any moment the ranks address DIFFERENT destinations (no incast on one NVLink port) */
 } B200AtmoPeerTargets;
 int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
                                 int row_begin, int row_end, const B200AtmoPeerTargets* targets, void* stream);

@@ -54,13 +54,19 @@ def test_no_cpu_fallback_without_a_device():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "godot_atmosphere_shader_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "pyoracle" not in text and "liboracle" not in text and "hostsim" not in text.replace(
-                    "tests/hostsim", ""), f"{f} references test infrastructure"
+    """Neither the package, nor the GDExtension wrapper, nor the C example reference the oracle, the compiled reference
+    shaders or the host simulation; the shipped libraries link neither."""
+    import subprocess
+    for top in ("godot_atmosphere_shader_b200", "gdextension", "examples", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".c", ".cpp", ".sh", ".inc")):
+                    text = open(os.path.join(dirpath, f)).read().replace("tests/hostsim", "")
+                    for word in ("pyoracle", "liboracle", "hostsim", "pyref", "libatmo_ref", "atmo_oracle", "from oracle", "import oracle"):
+                        assert word not in text, f"{top}/{f} references test infrastructure ({word})"
+    for so in ("libb200atmo.so", "libb200atmo_node.so"):
+        needed = subprocess.run(["readelf", "-d", os.path.join(ROOT, "godot_atmosphere_shader_b200", so)], capture_output=True, text=True).stdout
+        assert "oracle" not in needed and "atmo_ref" not in needed
 
 
 @pytest.mark.gpu

@@ -394,9 +394,9 @@ def run_ours(a, rank, world, local_rank):
         # (NVLS multicast when the fabric offers it) -- the render IS the all-gather, no collective pass
         from godot_atmosphere_shader_b200.sharding import SymmetricTiles, render_rays_and_gather_fused
         fused = {}
-        for label, use_mc, stagger in (("multicast", True, True), ("p2p", False, True), ("p2p_unstaggered", False, False)):
+        for label, use_mc, use_tma in (("multicast", True, False), ("p2p", False, False), ("p2p_tma", False, True)):
             try:
-                tiles = SymmetricTiles(world, n_rays, dev, use_multicast=use_mc, stagger=stagger)
+                tiles = SymmetricTiles(world, n_rays, dev, use_multicast=use_mc, use_tma=use_tma)
                 if use_mc and not tiles.multicast_ptr:
                     fused[label] = {"unavailable": "no NVLS multicast mapping on this fabric"}
                     continue

@@ -662,6 +662,7 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     }
     io.n_peers = t->n_peers;
     io.first_peer = (t->first_peer >= 0 && t->first_peer < t->n_peers) ? t->first_peer : 0;
+    io.use_tma = t->use_tma != 0;
     io.rgba_multicast = t->d_rgba_multicast;
     io.peer_offset = size_t(t->elem_offset);
     return B200ATMO_OK;

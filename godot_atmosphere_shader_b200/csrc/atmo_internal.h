@@ -84,6 +84,7 @@ struct RayIOPeers : RayIO {
     void* rgba_multicast;
     int n_peers;
     int first_peer;            // store loop starts here and wraps (ranks stagger their destinations)
+    int use_tma;               // ray kernel: stage the block's results in smem, one cp.async.bulk per peer
     size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
 };
 

@@ -235,6 +235,38 @@ __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevCo
     if (io.discard) io.discard[i] = disc ? 1 : 0;
 }
 
+// Peer variant with TMA bulk stores (RayIOPeers::use_tma): the block's 128 results are staged in shared memory and ONE
+// elected thread sends the 2 KB tile to every rank with cp.async.bulk (shared::cta -> global, the global address being the
+// peer mapping), instead of 128 threads x n_peers STG.128. No thread leaves before the barrier.
+template <int MODEL, int LIGHT>
+__global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_constant__ DevConsts c, const RayIOPeers io) {
+    __shared__ __align__(128) float4 s_out[kBlock];
+    const size_t base = blockIdx.x * size_t(kBlock);
+    const size_t i = base + threadIdx.x;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < io.n) {
+        const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
+        const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
+        shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
+    }
+    s_out[threadIdx.x] = out;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async (TMA) proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t left = io.n - base;
+        const unsigned bytes = unsigned(left < size_t(kBlock) ? left : size_t(kBlock)) * 16u;
+        const unsigned src = unsigned(__cvta_generic_to_shared(s_out));
+        int r = io.first_peer;
+        for (int k = 0; k < io.n_peers; ++k) {
+            float4* dst = static_cast<float4*>(io.rgba_peers[r]) + io.peer_offset + base;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+            r = (r + 1 == io.n_peers) ? 0 : r + 1;
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the tile has left shared memory and been written
+    }
+}
+
 // Frame: a warp covers an 8x4 pixel tile (coherent LUT / texture footprints, full 128 B store
 // segments per tile row), a block of 4 warps a 16x8 tile.
 template <int MODEL, int LIGHT, class IO>
@@ -317,7 +349,19 @@ cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_
     return launch_rays_t(c, io, scatter_model, light_mode, s);
 }
 cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s) {
-    return launch_rays_t(c, io, scatter_model, light_mode, s);
+    if (!io.use_tma || io.rgba_multicast) return launch_rays_t(c, io, scatter_model, light_mode, s);
+    if (io.n == 0) return cudaSuccess;
+    const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
+    if (scatter_model == B200ATMO_SCATTER_V1) {
+        if (light_mode == B200ATMO_LIGHT_NONE) render_rays_tma_peers_kernel<1, 0><<<grid, kBlock, 0, s>>>(c, io);
+        else if (light_mode == B200ATMO_LIGHT_CHEAP) render_rays_tma_peers_kernel<1, 1><<<grid, kBlock, 0, s>>>(c, io);
+        else render_rays_tma_peers_kernel<1, 2><<<grid, kBlock, 0, s>>>(c, io);
+    } else {
+        if (light_mode == B200ATMO_LIGHT_NONE) render_rays_tma_peers_kernel<0, 0><<<grid, kBlock, 0, s>>>(c, io);
+        else if (light_mode == B200ATMO_LIGHT_CHEAP) render_rays_tma_peers_kernel<0, 1><<<grid, kBlock, 0, s>>>(c, io);
+        else render_rays_tma_peers_kernel<0, 2><<<grid, kBlock, 0, s>>>(c, io);
+    }
+    return cudaGetLastError();
 }
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
     return launch_frame_t(c, io, scatter_model, light_mode, s);

@@ -86,7 +86,7 @@ def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int
 # ------------------------------------------------------------------------------------------------
 # fused render + all-gather over NVLink / NVSwitch peer memory (b200atmo_render_*_peers)
 # ------------------------------------------------------------------------------------------------
-def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_peer: int = 0):
+def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_peer: int = 0, use_tma: bool = False):
     """B200AtmoPeerTargets from the device addresses of one symmetric buffer as mapped in this process."""
     from .abi import MAX_PEERS, B200AtmoPeerTargets
 
@@ -102,6 +102,7 @@ def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_pe
     t.d_rgba_multicast = int(multicast_ptr) if multicast_ptr else None
     t.elem_offset = int(elem_offset)
     t.first_peer = int(first_peer) % len(ptrs)   # (rank + 1) % world staggers the ranks' destinations
+    t.use_tma = 1 if use_tma else 0
     return t
 
 
@@ -111,13 +112,15 @@ class SymmetricTiles:
     Rank r's render kernels store slot r of EVERY rank's buffer directly (`targets(rank)`), so after `barrier()` each GPU
     holds all tiles: the render is the all-gather. PyTorch is the plumbing (allocation, rendezvous, barrier) only."""
 
-    def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False, stagger: bool = True):
+    def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False, stagger: bool = True,
+                 use_tma: bool = False):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
         self.slots, self.rays_per_slot = int(slots), int(rays_per_slot)
         self.stagger = bool(stagger)
+        self.use_tma = bool(use_tma)
         group = group if group is not None else dist.group.WORLD
         self.tensor = symm_mem.empty((self.slots, self.rays_per_slot, 4), dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.tensor, group.group_name)
@@ -129,7 +132,7 @@ class SymmetricTiles:
 
     def targets(self, slot: int):
         return peer_targets(self.buffer_ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot,
-                            first_peer=(self.rank + 1) % self.world if self.stagger else 0)
+                            first_peer=(self.rank + 1) % self.world if self.stagger else 0, use_tma=self.use_tma)
 
     def barrier(self):
         """Stream-ordered inter-rank barrier on the current CUDA stream: after it, every rank's stores have landed here."""

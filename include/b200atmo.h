@@ -258,6 +258,9 @@ typedef struct B200AtmoPeerTargets {
     uint64_t elem_offset;                   /* float4 elements added to the pixel / ray index (this rank's slot) */
     int32_t first_peer;                     /* P2P path: index the store loop starts at (wraps around). Pass (rank + 1) % n_peers so
                                                that at any moment the ranks address DIFFERENT destinations (no incast on one NVLink port) */
+    int32_t use_tma;                        /* b200atmo_render_rays_peers, P2P path: != 0 stages each block's 128 results in shared
+                                               memory and sends them with one TMA bulk store (cp.async.bulk) per peer instead of one
+                                               STG.128 per thread and peer. Needs 16-byte aligned buffers and elem_offset. */
 } B200AtmoPeerTargets;
 int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
                                 int row_begin, int row_end, const B200AtmoPeerTargets* targets, void* stream);

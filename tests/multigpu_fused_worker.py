@@ -28,7 +28,7 @@ def main():
     ctx.upload_coverage_cube(scenes.coverage_cubemap(32, seed=1))
     stream = torch.cuda.current_stream().cuda_stream
     report = {}
-    for use_mc in (True, False):
+    for use_mc, use_tma in ((True, False), (False, False), (False, True)):
         # (1) weak scaling: every rank renders its own tile (orbiting camera), all ranks receive all tiles
         cam = scenes.camera_a(w, h, orbit_deg=30.0 * rank)
         d_depth = torch.from_numpy(scenes.synth_depth(cam, p, w, h)).to(dev)
@@ -40,13 +40,13 @@ def main():
         ctx.render_rays(fr, d_od, d_dj, n, mine, None, stream=stream)
         ref = torch.empty((world * n, 4), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(ref, mine)
-        tiles = sharding.SymmetricTiles(world, n, dev, use_multicast=use_mc)
+        tiles = sharding.SymmetricTiles(world, n, dev, use_multicast=use_mc, use_tma=use_tma)
         tiles.tensor.fill_(-1.0)
         tiles.barrier()
         out = sharding.render_rays_and_gather_fused(ctx, fr, d_od, d_dj, n, tiles, stream=stream)
         torch.cuda.synchronize()
-        assert torch.equal(out.view(world * n, 4), ref), f"rank {rank}: fused tiles differ from render + all-gather (multicast={use_mc})"
-        report[f"tiles_mc{int(use_mc)}"] = bool(tiles.multicast_ptr)
+        assert torch.equal(out.view(world * n, 4), ref), f"rank {rank}: fused tiles differ from render + all-gather (multicast={use_mc}, tma={use_tma})"
+        report[f"tiles_mc{int(use_mc)}_tma{int(use_tma)}"] = bool(tiles.multicast_ptr)
         # (2) strong scaling: ONE frame, rank g renders its row band into every rank's full frame
         cam1 = scenes.camera_a(w, h)
         d_depth1 = torch.from_numpy(scenes.synth_depth(cam1, p, w, h)).to(dev)
@@ -57,7 +57,7 @@ def main():
         frame_tiles.barrier()
         got = sharding.render_frame_sharded_fused(ctx, cam1, d_depth1, w, h, frame_tiles, stream=stream)
         torch.cuda.synchronize()
-        assert torch.equal(got, full), f"rank {rank}: band-sharded fused frame differs from the single-GPU frame (multicast={use_mc})"
+        assert torch.equal(got, full), f"rank {rank}: band-sharded fused frame differs from the single-GPU frame (multicast={use_mc}, tma={use_tma})"
         dist.barrier()
     ctx.close()
     if rank == 0:

@@ -333,6 +333,15 @@ def test_peer_store_paths_on_one_gpu(cuda_ctx_factory):
     ctx.render_rays_peers(fr, d_od, d_dj, h * w, t2)
     torch.cuda.synchronize()
     assert torch.equal(bufs[0][2], want) and torch.equal(bufs[2][2], want) and bool((bufs[1][2] == -7.0).all())
+    # TMA bulk-store flavour (cp.async.bulk from a shared-memory tile), ragged tail: n = 128*k + 37 rays
+    n_tail = 128 * 50 + 37
+    for b in bufs:
+        b.fill_(-7.0)
+    t3 = sharding.peer_targets([b.data_ptr() for b in bufs], elem_offset=h * w, first_peer=2, use_tma=True)
+    ctx.render_rays_peers(fr, d_od, d_dj, n_tail, t3)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[1][:n_tail], want[:n_tail]) and bool((b[1][n_tail:] == -7.0).all()) and bool((b[0] == -7.0).all())
     bad = sharding.peer_targets([bufs[0].data_ptr()])
     bad.n_peers = 9
     with pytest.raises(B200AtmoError):

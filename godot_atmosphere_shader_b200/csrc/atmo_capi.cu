@@ -46,6 +46,11 @@ struct b200atmo_ctx {
         size_t cap_depth = 0, cap_rgba = 0, cap_disc = 0;
         bool in_flight = false;
     } slots[B200ATMO_PIPELINE_SLOTS];
+    // frame front end: per-column / per-row tables of INV_PROJECTION_MATRIX * ndc for the last (w, h, projection)
+    float4* d_ray_tables = nullptr;
+    size_t cap_ray_tables = 0;
+    int tables_w = 0, tables_h = 0;
+    float tables_inv_proj[16] = {};
     uint64_t launches = 0;
     std::string last_error;
 };
@@ -285,6 +290,7 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
         cudaFree(sl.d_rgba);
         cudaFree(sl.d_disc);
     }
+    cudaFree(ctx->d_ray_tables);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
     cudaFree(ctx->d_lut_cells);
@@ -476,6 +482,31 @@ static int frame_consts(b200atmo_ctx* ctx, const B200AtmoCamera* cam, int w, int
     return B200ATMO_OK;
 }
 
+// Per-column / per-row tables of the frame front end (make_ray): rebuilt only when the frame size or the projection
+// changes (rare: resize, FOV change), then shared by every stream — hence the drain + synchronise on that path.
+static int frame_tables(b200atmo_ctx* ctx, const DevConsts& c, RayIO& io, cudaStream_t s) {
+    const size_t need = size_t(c.fw + c.fh) * sizeof(float4);
+    const bool stale = ctx->tables_w != c.fw || ctx->tables_h != c.fh ||
+                       std::memcmp(ctx->tables_inv_proj, c.inv_proj, sizeof(ctx->tables_inv_proj)) != 0;
+    if (stale) {
+        int rc = drain_slots(ctx);
+        if (rc != B200ATMO_OK) return rc;
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
+        if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_ray_tables), &ctx->cap_ray_tables, need)) != B200ATMO_OK) return rc;
+        ctx->tables_w = 0;
+        CU_TRY(ctx, launch_ray_tables(c, ctx->d_ray_tables, ctx->d_ray_tables + c.fw, s));
+        ctx->launches++;
+        CU_TRY(ctx, cudaStreamSynchronize(s));
+        ctx->tables_w = c.fw;
+        ctx->tables_h = c.fh;
+        std::memcpy(ctx->tables_inv_proj, c.inv_proj, sizeof(ctx->tables_inv_proj));
+    }
+    io.ray_col = ctx->d_ray_tables;
+    io.ray_row = ctx->d_ray_tables + c.fw;
+    return B200ATMO_OK;
+}
+
 int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
                           int row_end, float* d_rgba, uint8_t* d_discard, void* stream) {
     if (!ctx || !cam || !d_depth || !d_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame: NULL argument");
@@ -491,6 +522,7 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
     io.rgba = d_rgba;
     io.discard = d_discard;
     io.n = size_t(w) * h;
+    if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
     CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
@@ -514,6 +546,7 @@ int b200atmo_render_frame_composite_fmt(b200atmo_ctx* ctx, const B200AtmoCamera*
     io.color_inout = d_color_inout;
     io.color_format = color_format;
     io.n = size_t(w) * h;
+    if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
     CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
@@ -547,6 +580,7 @@ int b200atmo_composite_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, 
     io.color_inout = d_color;
     io.color_format = color_format;
     io.n = npx;
+    if ((rc = frame_tables(ctx, c, io, ctx->streams[0])) != B200ATMO_OK) return rc;
     // equal row bands alternating over two streams: the uploads of band k+1 (12 or 20 B/pixel) run while band k downloads
     // (8 or 16 B/pixel); PCIe is full duplex, so the slower direction bounds the frame
     const int bands = h >= 512 ? 8 : (h >= 256 ? 4 : 1);   // the upload is the longer leg here: finer bands shorten the tail
@@ -581,6 +615,7 @@ int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float
     io.out_origin_depth = d_origin_depth;
     io.out_dir_jitter = d_dir_jitter;
     io.n = size_t(w) * h;
+    if ((rc = frame_tables(ctx, c, io, static_cast<cudaStream_t>(stream))) != B200ATMO_OK) return rc;
     CU_TRY(ctx, launch_make_rays(c, io, static_cast<cudaStream_t>(stream)));
     ctx->launches++;
     if (frame_out) {
@@ -619,6 +654,7 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     io.rgba = d_rgba;
     io.discard = h_discard ? ctx->d_stage_disc : nullptr;
     io.n = npx;
+    if ((rc = frame_tables(ctx, c, io, ctx->streams[0])) != B200ATMO_OK) return rc;
     // Row bands, alternating over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band). The D2H of 16 B/px
     // is the PCIe-bound leg (4x the H2D), so the first band is small (the D2H engine starts early) and bands grow by
     // ~1.5x: each band's upload + kernel hides behind the previous band's download. Few bands: the host issues
@@ -682,6 +718,7 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
     if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
     io.depth = d_depth;
     io.n = size_t(w) * h;
+    if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
     CU_TRY(ctx, launch_render_frame_peers(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
@@ -731,6 +768,7 @@ int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* c
     io.rgba = sl.d_rgba;
     io.discard = h_discard ? static_cast<uint8_t*>(sl.d_disc) : nullptr;
     io.n = npx;
+    if ((rc = frame_tables(ctx, c, io, sl.stream)) != B200ATMO_OK) return rc;
     sl.in_flight = true;   // from the first enqueue on the host buffers are in use, also if a later enqueue fails
     CU_TRY(ctx, cudaMemcpyAsync(sl.d_depth, h_depth, npx * sizeof(float), cudaMemcpyHostToDevice, sl.stream));
     CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, sl.stream));

@@ -628,10 +628,30 @@ B200_DEV bool far_box_covers(const DevConsts& c, f3 o, f3 d, float linear_depth)
 }
 
 // main:128-142 — ray generation from the depth texture (exact arithmetic, shader op order)
-B200_DEV void make_ray(const DevConsts& c, int x, int y, float nonlinear_depth, f3& o, f3& d, float& linear_depth, float& jitter) {
-    const float su = (float(x) + 0.5f) / float(c.fw), sv = (float(y) + 0.5f) / float(c.fh);  // SCREEN_UV
+// The x- and y-terms of INV_PROJECTION_MATRIX * vec4(ndc, 1) depend on the column / the row only: ray_tables_kernel
+// evaluates them once per frame size with the same operations in the same order, so the sums below are bit-identical to
+// mat4_mul(inv_proj, ndc.x, ndc.y, depth, 1) = ((m0*x + m4*y) + m8*z) + m12*1 while the pixel saves two IEEE divisions,
+// the ndc arithmetic and 8 of the 16 products.
+B200_DEV float4 ray_col_entry(const DevConsts& c, int x) {
+    const float su = (float(x) + 0.5f) / float(c.fw);          // SCREEN_UV.x of the fragment centre
+    const float nx = su * 2.0f - 1.0f;                          // :130
+    return make_float4(c.inv_proj[0] * nx, c.inv_proj[1] * nx, c.inv_proj[2] * nx, c.inv_proj[3] * nx);
+}
+B200_DEV float4 ray_row_entry(const DevConsts& c, int y) {
+    const float sv = (float(y) + 0.5f) / float(c.fh);
+    const float ny = sv * 2.0f - 1.0f;
+    return make_float4(c.inv_proj[4] * ny, c.inv_proj[5] * ny, c.inv_proj[6] * ny, c.inv_proj[7] * ny);
+}
+
+B200_DEV void make_ray(const DevConsts& c, int x, int y, float nonlinear_depth, f3& o, f3& d, float& linear_depth, float& jitter,
+                       const float4* ray_col = nullptr, const float4* ray_row = nullptr) {
+    const float4 cx = ray_col ? ldg4(ray_col + x) : ray_col_entry(c, x);
+    const float4 cy = ray_row ? ldg4(ray_row + y) : ray_row_entry(c, y);
     float vc[4], wc[4];
-    mat4_mul(c.inv_proj, su * 2.0f - 1.0f, sv * 2.0f - 1.0f, nonlinear_depth, 1.0f, vc);  // :130-131
+    vc[0] = cx.x + cy.x + c.inv_proj[8] * nonlinear_depth + c.inv_proj[12] * 1.0f;   // :130-131
+    vc[1] = cx.y + cy.y + c.inv_proj[9] * nonlinear_depth + c.inv_proj[13] * 1.0f;
+    vc[2] = cx.z + cy.z + c.inv_proj[10] * nonlinear_depth + c.inv_proj[14] * 1.0f;
+    vc[3] = cx.w + cy.w + c.inv_proj[11] * nonlinear_depth + c.inv_proj[15] * 1.0f;
     mat4_mul(c.inv_view_ray, vc[0], vc[1], vc[2], vc[3], wc);                             // :134
     const f3 pos_world = mk3(wc[0] / wc[3], wc[1] / wc[3], wc[2] / wc[3]);                // :135
     const f3 dc = ld3(c.cam_pos_world) - pos_world;

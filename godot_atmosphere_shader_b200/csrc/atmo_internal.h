@@ -75,6 +75,11 @@ struct RayIO {
     void* out_origin_depth;    // make_rays only
     void* out_dir_jitter;
     size_t n;
+    // frame front end: per-column / per-row partial products of INV_PROJECTION_MATRIX * ndc, hoisted out of the pixel
+    // (ray_tables_kernel); null = compute inline. Appended AFTER n: the offsets of the fields above must not move (the
+    // ptxas schedule of the march loop depends on them).
+    const float4* ray_col;     // [fw]  m[0..3] * ndc.x(x)
+    const float4* ray_row;     // [fh]  m[4..7] * ndc.y(y)
 };
 // fused render + all-gather (b200atmo_render_*_peers): the result goes to the same symmetric buffer on every GPU instead
 // of `rgba`: one multimem store when the NVLS multicast mapping is given, else one P2P store per peer. A separate
@@ -99,6 +104,7 @@ cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, i
 cudaError_t launch_render_frame_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
+cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, cudaStream_t s);
 #endif
 
 }  // namespace b200atmo

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
     const size_t i = size_t(y) * c.fw + x;
     f3 o, d;
     float linear_depth, jitter;
-    make_ray(c, x, y, __ldcs(io.depth + i), o, d, linear_depth, jitter);
+    make_ray(c, x, y, __ldcs(io.depth + i), o, d, linear_depth, jitter, io.ray_col, io.ray_row);
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     bool disc = true;
     if (!(c.clip_box_half > 0.0f) || far_box_covers(c, o, d, linear_depth))  // MODE_FAR: outside the proxy cube = not rasterised
@@ -314,9 +314,21 @@ __global__ void __launch_bounds__(kBlock) make_rays_kernel(const __grid_constant
     const int x = int(i % size_t(c.fw)), y = int(i / size_t(c.fw));
     f3 o, d;
     float linear_depth, jitter;
-    make_ray(c, x, y, io.depth[i], o, d, linear_depth, jitter);
+    make_ray(c, x, y, io.depth[i], o, d, linear_depth, jitter, io.ray_col, io.ray_row);
     static_cast<float4*>(io.out_origin_depth)[i] = make_float4(o.x, o.y, o.z, linear_depth);
     static_cast<float4*>(io.out_dir_jitter)[i] = make_float4(d.x, d.y, d.z, jitter);
+}
+
+// Per-column / per-row tables of the frame front end (see make_ray): fw + fh threads, once per (size, projection).
+__global__ void __launch_bounds__(256) ray_tables_kernel(const __grid_constant__ DevConsts c, float4* __restrict__ col,
+                                                          float4* __restrict__ row) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < c.fw) col[i] = ray_col_entry(c, i);
+    else if (i < c.fw + c.fh) row[i - c.fw] = ray_row_entry(c, i - c.fw);
+}
+cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, cudaStream_t s) {
+    ray_tables_kernel<<<(c.fw + c.fh + 255) / 256, 256, 0, s>>>(c, d_col, d_row);
+    return cudaGetLastError();
 }
 
 #define B200ATMO_DISPATCH(KERNEL, IO, GRID, ...)                                                              \

@@ -11,7 +11,8 @@
 // shader files where they lie under /root/reference as C++ (a purely syntactic rewrite + a header of GLSL types and
 // built-ins) into oracle/_ref/libatmo_ref.so, and tests/test_reference_pin.py requires this file (T=float) to equal
 // it BIT FOR BIT — LUT, discard masks, fp32 RGBA — for all 7 shipped entry shaders, the BASELINE scale-ups, corner
-// cameras and random scenes; a mutation test shows the comparison has teeth. What stays unpinned is what the
+// cameras and random scenes (and T=double to equal the same sources compiled with `float` = double,
+// libatmo_ref64.so); a mutation test shows the comparison has teeth. What stays unpinned is what the
 // reference leaves to the engine / GPU (the rounding of GLSL built-ins, texture filtering): defined below, used by
 // both sides. Further pins: known-answer tests derived by hand from the shader source (tests/test_oracle_kat.py), the
 // fp64 instantiation (same template, T=double), self-generated golden vectors (tests/golden/, generator committed).

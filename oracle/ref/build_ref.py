@@ -13,7 +13,8 @@ The rewrite touches syntax only (no expression is reordered, no constant changed
   * `#include "x"`               -> the file's text, recursively (its own #ifndef guards stay in charge)
   * `shader_type` / `render_mode` lines removed; `uniform T n : hints = v;` -> `static T n = v;`; `varying T n;` -> `static T n;`
   * `out T n` / `inout T n` parameters -> `T& n`; `in T n` -> `T n`; a trailing comma before `)` removed
-  * float literals get an `f` suffix (GLSL literals are fp32; C++ ones would be double)
+  * float literals get an `f` suffix (GLSL literals are fp32; C++ ones would be double), and the keyword `float` is a macro
+    for the library's real type: fp32 in libatmo_ref.so (THE reference), double in its twin libatmo_ref64.so (literals unsuffixed)
   * swizzles of 2-4 components (`.xyz`, `.rgb`, `.xz` ...) -> accessor calls (`.xyz()`); only reads occur in the sources
   * `discard;` -> sets the driver's flag and returns
   * `#define ATMOSPHERE_RAYMARCH_STEPS n` / `CLOUDS_MAX_RAYMARCH_STEPS n` -> a runtime variable initialised to n
@@ -59,8 +60,8 @@ def inline_includes(path, root):
     return "\n".join(out)
 
 
-def rewrite(text):
-    """GDShader -> C++ (syntax only; see the module docstring)."""
+def rewrite(text, real64=False):
+    """GDShader -> C++ (syntax only; see the module docstring). real64: literals stay double (the fp64 twin)."""
     n_subs = {}
 
     def sub(pattern, repl, s, key, flags=0):
@@ -74,7 +75,8 @@ def rewrite(text):
     text = sub(r"\b(?:inout|out)\s+(\w+)\s+(\w+)", r"\1& \2", text, "out/inout")
     text = sub(r"\bin\s+(?=(?:vec[234]|float|int|bool|mat[234])\b)", "", text, "in")
     text = sub(r",(\s*)\)", r"\1)", text, "trailing comma")
-    text = sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?)(?![\w.])", r"\1f", text, "float literal")
+    if not real64:
+        text = sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?)(?![\w.])", r"\1f", text, "float literal")
     text = sub(r"\.([xyzw]{2,4}|[rgba]{2,4})\b(?!\s*\()", r".\1()", text, "swizzle")
     text = sub(r"\bdiscard\s*;", "{ ref_discarded = true; return; }", text, "discard")
     for macro in STEP_MACROS:
@@ -91,9 +93,9 @@ def rewrite(text):
     return text, n_subs
 
 
-def gen_entry(root, name):
+def gen_entry(root, name, real64=False):
     path = os.path.join(root, SHADERS, name + ".gdshader")
-    body, subs = rewrite(inline_includes(path, root))
+    body, subs = rewrite(inline_includes(path, root), real64)
     src = f"""// GENERATED by oracle/ref/build_ref.py from {SHADERS}/{name}.gdshader — do not edit, do not commit.
 #include "glsl_compat.hpp"
 #define REF_ENTRY {name}
@@ -102,7 +104,9 @@ namespace ref_{name} {{
 GLSL_USING
 #include "ref_builtins.inc"
 // ------------------------------------------------ reference shader text (syntactic rewrite) ------------------------
+#define float real   /* the shader's `float`: fp32 in libatmo_ref.so, double in the fp64 twin libatmo_ref64.so */
 {body}
+#undef float
 // ------------------------------------------------ end of reference shader text --------------------------------------
 #include "ref_driver.inc"
 }}  // namespace
@@ -110,16 +114,18 @@ GLSL_USING
     return src, subs
 
 
-def gen_bake(root):
+def gen_bake(root, real64=False):
     path = os.path.join(root, SHADERS, "optical_depth.gdshader")
-    body, subs = rewrite(inline_includes(path, root))
+    body, subs = rewrite(inline_includes(path, root), real64)
     src = f"""// GENERATED by oracle/ref/build_ref.py from {SHADERS}/optical_depth.gdshader — do not edit, do not commit.
 #include "glsl_compat.hpp"
 namespace ref_optical_depth {{
 GLSL_USING
 #include "ref_builtins.inc"
 // ------------------------------------------------ reference shader text (syntactic rewrite) ------------------------
+#define float real   /* the shader's `float`: fp32 in libatmo_ref.so, double in the fp64 twin libatmo_ref64.so */
 {body}
+#undef float
 // ------------------------------------------------ end of reference shader text --------------------------------------
 #include "ref_bake_driver.inc"
 }}  // namespace
@@ -140,40 +146,44 @@ def build(reference="/root/reference", verbose=True, out_dir=None, keep_sources=
     work = keep_sources or tempfile.mkdtemp(prefix="b200atmo_ref_")
     os.makedirs(work, exist_ok=True)
     try:
-        sources = []
-        for name in ENTRY_SHADERS:
-            src, subs = gen_entry(reference, name)
-            p = os.path.join(work, f"gen_{name}.cpp")
+        libs = []
+        for real64 in (False, True):
+            tag = "64" if real64 else ""
+            sources = []
+            for name in ENTRY_SHADERS:
+                src, subs = gen_entry(reference, name, real64)
+                p = os.path.join(work, f"gen{tag}_{name}.cpp")
+                open(p, "w").write(src)
+                sources.append(p)
+                if verbose and not real64:
+                    print(f"  {name}: " + ", ".join(f"{k} x{v}" for k, v in subs.items() if v))
+            src, subs = gen_bake(reference, real64)
+            p = os.path.join(work, f"gen{tag}_optical_depth.cpp")
             open(p, "w").write(src)
             sources.append(p)
+            sources.append(os.path.join(HERE, "ref_dispatch.cpp"))
+            lib = os.path.join(out_root, f"libatmo_ref{tag}.so")
+            cxx = os.environ.get("CXX", "g++")
+            flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-Wno-unused-variable",
+                     "-Wno-unused-function", "-Wno-unused-but-set-variable", "-I" + HERE] + (["-DGLSL_REAL=double"] if real64 else [])
+            objs, procs = [], []
+            for s in sources:
+                o = os.path.join(work, f"o{tag}_" + os.path.basename(s)[:-4] + ".o")
+                objs.append(o)
+                procs.append((s, subprocess.Popen([cxx] + flags + ["-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            failed = False
+            for s, pr in procs:
+                out, _ = pr.communicate()
+                if pr.returncode != 0:
+                    failed = True
+                    sys.stderr.write(f"--- {s}\n{out[-6000:]}\n")
+            if failed:
+                raise RuntimeError("oracle/_ref: compiling the rewritten reference shaders failed")
+            subprocess.check_call([cxx, "-shared", "-pthread", "-o", lib] + objs)
             if verbose:
-                print(f"  {name}: " + ", ".join(f"{k} x{v}" for k, v in subs.items() if v))
-        src, subs = gen_bake(reference)
-        p = os.path.join(work, "gen_optical_depth.cpp")
-        open(p, "w").write(src)
-        sources.append(p)
-        sources.append(os.path.join(HERE, "ref_dispatch.cpp"))
-        lib = os.path.join(out_root, "libatmo_ref.so")
-        cxx = os.environ.get("CXX", "g++")
-        flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-Wno-unused-variable",
-                 "-Wno-unused-function", "-Wno-unused-but-set-variable", "-I" + HERE]
-        objs, procs = [], []
-        for s in sources:
-            o = os.path.join(work, os.path.basename(s)[:-4] + ".o")
-            objs.append(o)
-            procs.append((s, subprocess.Popen([cxx] + flags + ["-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        failed = False
-        for s, pr in procs:
-            out, _ = pr.communicate()
-            if pr.returncode != 0:
-                failed = True
-                sys.stderr.write(f"--- {s}\n{out[-6000:]}\n")
-        if failed:
-            raise RuntimeError("oracle/_ref: compiling the rewritten reference shaders failed")
-        subprocess.check_call([cxx, "-shared", "-pthread", "-o", lib] + objs)
-        if verbose:
-            print(f"built {lib}")
-        return lib
+                print(f"built {lib}")
+            libs.append(lib)
+        return libs[0]
     finally:
         if not keep_sources:
             shutil.rmtree(work, ignore_errors=True)

@@ -23,51 +23,56 @@
 
 #include "../atmo_oracle.hpp"
 
+#ifndef GLSL_REAL
+#define GLSL_REAL float
+#endif
+
 namespace glsl {
 
+typedef GLSL_REAL real;   // float: the shader's precision (THE reference); double: its fp64 twin (rounding-error bound)
 typedef unsigned int uint;
 
 struct vec2 {
-    union { float x, r; };
-    union { float y, g; };
+    union { real x, r; };
+    union { real y, g; };
     vec2() : x(0.f), y(0.f) {}
-    explicit vec2(float s) : x(s), y(s) {}
-    vec2(float x_, float y_) : x(x_), y(y_) {}
+    explicit vec2(real s) : x(s), y(s) {}
+    vec2(real x_, real y_) : x(x_), y(y_) {}
 };
 struct vec3 {
-    union { float x, r; };
-    union { float y, g; };
-    union { float z, b; };
+    union { real x, r; };
+    union { real y, g; };
+    union { real z, b; };
     vec3() : x(0.f), y(0.f), z(0.f) {}
-    explicit vec3(float s) : x(s), y(s), z(s) {}
-    vec3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
-    vec3(vec2 v, float z_) : x(v.x), y(v.y), z(z_) {}
+    explicit vec3(real s) : x(s), y(s), z(s) {}
+    vec3(real x_, real y_, real z_) : x(x_), y(y_), z(z_) {}
+    vec3(vec2 v, real z_) : x(v.x), y(v.y), z(z_) {}
     vec2 xy() const { return vec2(x, y); }
     vec2 xz() const { return vec2(x, z); }
     vec3 xyz() const { return *this; }
     vec3 rgb() const { return *this; }
 };
 struct vec4 {
-    union { float x, r; };
-    union { float y, g; };
-    union { float z, b; };
-    union { float w, a; };
+    union { real x, r; };
+    union { real y, g; };
+    union { real z, b; };
+    union { real w, a; };
     vec4() : x(0.f), y(0.f), z(0.f), w(0.f) {}
-    explicit vec4(float s) : x(s), y(s), z(s), w(s) {}
-    vec4(float x_, float y_, float z_, float w_) : x(x_), y(y_), z(z_), w(w_) {}
-    vec4(vec3 v, float w_) : x(v.x), y(v.y), z(v.z), w(w_) {}
-    vec4(vec2 v, float z_, float w_) : x(v.x), y(v.y), z(z_), w(w_) {}
+    explicit vec4(real s) : x(s), y(s), z(s), w(s) {}
+    vec4(real x_, real y_, real z_, real w_) : x(x_), y(y_), z(z_), w(w_) {}
+    vec4(vec3 v, real w_) : x(v.x), y(v.y), z(v.z), w(w_) {}
+    vec4(vec2 v, real z_, real w_) : x(v.x), y(v.y), z(z_), w(w_) {}
     vec2 xy() const { return vec2(x, y); }
     vec3 xyz() const { return vec3(x, y, z); }
     vec3 rgb() const { return vec3(x, y, z); }
-    float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
-    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    real& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    real operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
 };
 struct ivec2 {
     int x, y;
     explicit ivec2(int s) : x(s), y(s) {}
     ivec2(int x_, int y_) : x(x_), y(y_) {}
-    explicit ivec2(vec2 v) : x(int(v.x)), y(int(v.y)) {}   // float -> int conversion truncates toward zero
+    explicit ivec2(vec2 v) : x(int(v.x)), y(int(v.y)) {}   // real -> int conversion truncates toward zero
 };
 inline ivec2 operator&(ivec2 a, ivec2 b) { return ivec2(a.x & b.x, a.y & b.y); }
 
@@ -77,37 +82,37 @@ inline vec2 operator-(vec2 a, vec2 b) { return vec2(a.x - b.x, a.y - b.y); }
 inline vec2 operator*(vec2 a, vec2 b) { return vec2(a.x * b.x, a.y * b.y); }
 inline vec2 operator/(vec2 a, vec2 b) { return vec2(a.x / b.x, a.y / b.y); }
 inline vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
-inline vec2 operator*(vec2 a, float s) { return vec2(a.x * s, a.y * s); }
-inline vec2 operator*(float s, vec2 a) { return vec2(s * a.x, s * a.y); }
-inline vec2 operator/(vec2 a, float s) { return vec2(a.x / s, a.y / s); }
-inline vec2 operator+(vec2 a, float s) { return vec2(a.x + s, a.y + s); }
-inline vec2 operator-(vec2 a, float s) { return vec2(a.x - s, a.y - s); }
+inline vec2 operator*(vec2 a, real s) { return vec2(a.x * s, a.y * s); }
+inline vec2 operator*(real s, vec2 a) { return vec2(s * a.x, s * a.y); }
+inline vec2 operator/(vec2 a, real s) { return vec2(a.x / s, a.y / s); }
+inline vec2 operator+(vec2 a, real s) { return vec2(a.x + s, a.y + s); }
+inline vec2 operator-(vec2 a, real s) { return vec2(a.x - s, a.y - s); }
 inline vec2& operator+=(vec2& a, vec2 b) { a = a + b; return a; }
-inline vec2& operator*=(vec2& a, float s) { a = a * s; return a; }
+inline vec2& operator*=(vec2& a, real s) { a = a * s; return a; }
 
 inline vec3 operator+(vec3 a, vec3 b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline vec3 operator-(vec3 a, vec3 b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline vec3 operator*(vec3 a, vec3 b) { return vec3(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline vec3 operator/(vec3 a, vec3 b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
 inline vec3 operator-(vec3 a) { return vec3(-a.x, -a.y, -a.z); }
-inline vec3 operator*(vec3 a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
-inline vec3 operator*(float s, vec3 a) { return vec3(s * a.x, s * a.y, s * a.z); }
-inline vec3 operator/(vec3 a, float s) { return vec3(a.x / s, a.y / s, a.z / s); }
-inline vec3 operator/(float s, vec3 a) { return vec3(s / a.x, s / a.y, s / a.z); }
-inline vec3 operator+(vec3 a, float s) { return vec3(a.x + s, a.y + s, a.z + s); }
-inline vec3 operator-(vec3 a, float s) { return vec3(a.x - s, a.y - s, a.z - s); }
+inline vec3 operator*(vec3 a, real s) { return vec3(a.x * s, a.y * s, a.z * s); }
+inline vec3 operator*(real s, vec3 a) { return vec3(s * a.x, s * a.y, s * a.z); }
+inline vec3 operator/(vec3 a, real s) { return vec3(a.x / s, a.y / s, a.z / s); }
+inline vec3 operator/(real s, vec3 a) { return vec3(s / a.x, s / a.y, s / a.z); }
+inline vec3 operator+(vec3 a, real s) { return vec3(a.x + s, a.y + s, a.z + s); }
+inline vec3 operator-(vec3 a, real s) { return vec3(a.x - s, a.y - s, a.z - s); }
 inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 inline vec3& operator-=(vec3& a, vec3 b) { a = a - b; return a; }
 inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
-inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
+inline vec3& operator*=(vec3& a, real s) { a = a * s; return a; }
 
 inline vec4 operator+(vec4 a, vec4 b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 inline vec4 operator-(vec4 a, vec4 b) { return vec4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 inline vec4 operator*(vec4 a, vec4 b) { return vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 inline vec4 operator/(vec4 a, vec4 b) { return vec4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w); }
-inline vec4 operator*(vec4 a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
-inline vec4 operator*(float s, vec4 a) { return vec4(s * a.x, s * a.y, s * a.z, s * a.w); }
-inline vec4 operator/(vec4 a, float s) { return vec4(a.x / s, a.y / s, a.z / s, a.w / s); }
+inline vec4 operator*(vec4 a, real s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline vec4 operator*(real s, vec4 a) { return vec4(s * a.x, s * a.y, s * a.z, s * a.w); }
+inline vec4 operator/(vec4 a, real s) { return vec4(a.x / s, a.y / s, a.z / s, a.w / s); }
 
 // ---- matrices (column-major, m[col][row]) ------------------------------------------------------------------------
 struct mat2 {
@@ -136,71 +141,80 @@ inline mat4 operator*(const mat4& a, const mat4& b) {
 }
 
 // ---- built-in functions --------------------------------------------------------------------------------------------
-inline float max(float a, float b) { return std::max(a, b); }
-inline float min(float a, float b) { return std::min(a, b); }
-inline float abs(float a) { return std::fabs(a); }
+inline real max(real a, real b) { return std::max(a, b); }
+inline real min(real a, real b) { return std::min(a, b); }
+inline real abs(real a) { return std::fabs(a); }
 inline vec3 abs(vec3 a) { return vec3(std::fabs(a.x), std::fabs(a.y), std::fabs(a.z)); }
-inline float sqrt(float a) { return std::sqrt(a); }
-inline float exp(float a) { return std::exp(a); }
+inline real sqrt(real a) { return std::sqrt(a); }
+inline real exp(real a) { return std::exp(a); }
 inline vec3 exp(vec3 a) { return vec3(std::exp(a.x), std::exp(a.y), std::exp(a.z)); }
-inline float pow(float x, float y) { return x <= 0.0f ? 0.0f : std::pow(x, y); }   // GLSL: undefined for x < 0 (see header)
-inline float clamp(float x, float lo, float hi) { return std::min(std::max(x, lo), hi); }
+inline real pow(real x, real y) { return x <= 0.0f ? 0.0f : std::pow(x, y); }   // GLSL: undefined for x < 0 (see header)
+inline real clamp(real x, real lo, real hi) { return std::min(std::max(x, lo), hi); }
 inline vec3 clamp(vec3 v, vec3 lo, vec3 hi) { return vec3(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z)); }
-inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
-inline vec3 mix(vec3 a, vec3 b, float t) { return vec3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
-inline vec4 mix(vec4 a, vec4 b, float t) { return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t)); }
-inline float smoothstep(float e0, float e1, float x) {
-    float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+inline real mix(real a, real b, real t) { return a * (1.0f - t) + b * t; }
+inline vec3 mix(vec3 a, vec3 b, real t) { return vec3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
+inline vec4 mix(vec4 a, vec4 b, real t) { return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t)); }
+inline real smoothstep(real e0, real e1, real x) {
+    real t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
     return t * t * (3.0f - 2.0f * t);
 }
-inline float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
-inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline float length(vec2 a) { return std::sqrt(dot(a, a)); }
-inline float length(vec3 a) { return std::sqrt(dot(a, a)); }
-inline float distance(vec3 a, vec3 b) { return length(a - b); }
+inline real dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+inline real dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline real length(vec2 a) { return std::sqrt(dot(a, a)); }
+inline real length(vec3 a) { return std::sqrt(dot(a, a)); }
+inline real distance(vec3 a, vec3 b) { return length(a - b); }
 inline vec3 normalize(vec3 a) { return a / length(a); }
-inline uint floatBitsToUint(float f) {
+// fp32 bit pattern of the argument; the fp64 twin also keeps the unrounded value (the RGBA8 viewport encoding of
+// optical_depth.gdshader is an fp32 container, the twin's bake reads the value from here instead)
+inline real& last_float_bits_arg() {
+    static thread_local real v = real(0);
+    return v;
+}
+inline uint floatBitsToUint(real f) {
+    last_float_bits_arg() = f;
+    const float g = float(f);
     uint u;
-    std::memcpy(&u, &f, 4);
+    std::memcpy(&u, &g, 4);
     return u;
 }
 
 // ---- samplers: what the engine binds; fetches follow the oracle-defined conventions ----------------------------------
 struct sampler2D {
     enum Kind { UNSET, LUT_F32, DEPTH_F32, L8 } kind = UNSET;
-    const float* f32 = nullptr;   // LUT: 256 x 256 (linear filter, clamp); DEPTH: w x h (nearest)
+    const real* lut = nullptr;    // LUT: 256 x 256 (linear filter, clamp)
+    const float* f32 = nullptr;   // DEPTH: w x h fp32 as handed over by the engine (nearest)
     const uint8_t* u8 = nullptr;  // L8: w x h (texelFetch only)
     int w = 0, h = 0;
 };
 struct sampler3D {
-    const oracle::Uniforms<float>* tex = nullptr;   // holds the shape texture pointers (oracle::sample_shape3d)
+    const oracle::Uniforms<real>* tex = nullptr;   // holds the shape texture pointers (oracle::sample_shape3d)
 };
 struct samplerCube {
-    const oracle::Uniforms<float>* tex = nullptr;   // holds the padded cube (oracle::cube_build_padded layout)
+    const oracle::Uniforms<real>* tex = nullptr;   // holds the padded cube (oracle::cube_build_padded layout)
 };
 inline vec4 texture(const sampler2D& s, vec2 uv) {
     if (s.kind == sampler2D::LUT_F32) {
-        const float v = oracle::sample_lut<float>(s.f32, uv.x, uv.y);
+        const real v = oracle::sample_lut<real>(s.lut, uv.x, uv.y);
         return vec4(v, 0.f, 0.f, 1.f);
     }
     if (s.kind == sampler2D::DEPTH_F32) {   // hint_depth_texture: nearest texel under the fragment
-        const int ix = std::min(std::max(int(std::floor(uv.x * float(s.w))), 0), s.w - 1);
-        const int iy = std::min(std::max(int(std::floor(uv.y * float(s.h))), 0), s.h - 1);
-        return vec4(s.f32[size_t(iy) * s.w + ix], 0.f, 0.f, 1.f);
+        const int ix = std::min(std::max(int(std::floor(uv.x * real(s.w))), 0), s.w - 1);
+        const int iy = std::min(std::max(int(std::floor(uv.y * real(s.h))), 0), s.h - 1);
+        return vec4(real(s.f32[size_t(iy) * s.w + ix]), 0.f, 0.f, 1.f);
     }
     return vec4(1.f);   // unset sampler = white
 }
 inline vec4 texelFetch(const sampler2D& s, ivec2 p, int /*lod*/) {
     if (s.kind != sampler2D::L8) return vec4(0.f, 0.f, 0.f, 1.f);   // no blue-noise texture bound: jitter 0 (oracle convention)
-    const float v = float(s.u8[size_t(p.y) * s.w + p.x]) / 255.0f;
+    const real v = real(s.u8[size_t(p.y) * s.w + p.x]) / 255.0f;
     return vec4(v, v, v, 1.f);
 }
 inline vec4 texture(const sampler3D& s, vec3 p) {
-    const float v = s.tex ? oracle::sample_shape3d<float>(*s.tex, oracle::vec3<float>{p.x, p.y, p.z}) : 1.0f;
+    const real v = s.tex ? oracle::sample_shape3d<real>(*s.tex, oracle::vec3<real>{p.x, p.y, p.z}) : 1.0f;
     return vec4(v, v, v, 1.f);
 }
 inline vec4 texture(const samplerCube& s, vec3 d) {
-    const float v = s.tex ? oracle::sample_cube<float>(*s.tex, oracle::vec3<float>{d.x, d.y, d.z}) : 1.0f;
+    const real v = s.tex ? oracle::sample_cube<real>(*s.tex, oracle::vec3<real>{d.x, d.y, d.z}) : 1.0f;
     return vec4(v, v, v, 1.f);
 }
 
@@ -209,7 +223,7 @@ inline vec4 texture(const samplerCube& s, vec3 d) {
 // Brought into each generated namespace by using-DECLARATIONS (they hide ::sqrt, ::exp, ::pow ... of <cmath> for
 // unqualified calls, which a using-directive would not).
 #define GLSL_USING                                                                                                     \
-    using glsl::uint; using glsl::vec2; using glsl::vec3; using glsl::vec4; using glsl::ivec2; using glsl::mat2; using glsl::mat4;     \
+    using glsl::real; using glsl::uint; using glsl::vec2; using glsl::vec3; using glsl::vec4; using glsl::ivec2; using glsl::mat2; using glsl::mat4;     \
     using glsl::sampler2D; using glsl::sampler3D; using glsl::samplerCube; using glsl::max; using glsl::min; using glsl::abs;          \
     using glsl::sqrt; using glsl::exp; using glsl::pow; using glsl::clamp; using glsl::mix; using glsl::smoothstep; using glsl::dot;   \
     using glsl::length; using glsl::distance; using glsl::normalize; using glsl::floatBitsToUint; using glsl::texture;                \

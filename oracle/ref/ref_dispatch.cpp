@@ -12,8 +12,8 @@ struct RefVariant {
 };
 #define REF_DECL(name)                                                                                                        \
     extern "C" void ref_##name##_defines(int out[4]);                                                                         \
-    extern "C" void ref_##name##_render_frame_f32(const B200AtmoParams*, const RefVariant*, const B200AtmoCamera*, const RefTextures*, \
-                                                  const float*, int, int, int, int, int, float*, uint8_t*, int);
+    extern "C" void ref_##name##_render_frame(const B200AtmoParams*, const RefVariant*, const B200AtmoCamera*, const RefTextures*, \
+                                                  const float*, int, int, int, int, int, void*, uint8_t*, int);
 REF_DECL(planet_atmosphere_no_clouds)
 REF_DECL(planet_atmosphere_clouds)
 REF_DECL(planet_atmosphere_clouds_high)
@@ -25,14 +25,14 @@ REF_DECL(planet_atmosphere_v1_clouds_high)
 namespace {
 typedef void (*DefinesFn)(int[4]);
 typedef void (*RenderFn)(const B200AtmoParams*, const RefVariant*, const B200AtmoCamera*, const RefTextures*, const float*, int, int,
-                         int, int, int, float*, uint8_t*, int);
+                         int, int, int, void*, uint8_t*, int);
 struct Entry {
     const char* name;
     DefinesFn defines;
     RenderFn render;
     int lite, atmo_steps, cloud_steps, rm;   // captured at load time, before any render changes the step variables
 };
-#define REF_ENTRY_ROW(n) {#n, ref_##n##_defines, ref_##n##_render_frame_f32, 0, 0, 0, 0}
+#define REF_ENTRY_ROW(n) {#n, ref_##n##_defines, ref_##n##_render_frame, 0, 0, 0, 0}
 Entry g_entries[] = {
     REF_ENTRY_ROW(planet_atmosphere_no_clouds),    REF_ENTRY_ROW(planet_atmosphere_clouds),
     REF_ENTRY_ROW(planet_atmosphere_clouds_high),  REF_ENTRY_ROW(planet_atmosphere_clouds_high_rm),
@@ -62,11 +62,12 @@ int ref_entry_defines(int i, int out[4]) {
     return 0;
 }
 
+// rgba: float[h*w*4] in libatmo_ref.so, double[h*w*4] in libatmo_ref64.so (ref_bake_real_size() tells which).
 // Renders with entry shader `name`, or (name == NULL) with the first shipped shader whose feature #defines match the
 // variant (step counts are runtime values in the compiled shaders). Returns 0, or -1 if there is no such shader.
-int ref_render_frame_f32(const char* name, const B200AtmoParams* p, const RefVariant* v, const B200AtmoCamera* cam,
+int ref_render_frame(const char* name, const B200AtmoParams* p, const RefVariant* v, const B200AtmoCamera* cam,
                          const RefTextures* tex, const float* depth, int w, int h, int row_begin, int row_end, int row_stride,
-                         float* rgba, uint8_t* discard, int threads) {
+                         void* rgba, uint8_t* discard, int threads) {
     for (const Entry& e : g_entries) {
         if (name) {
             if (std::strcmp(name, e.name) != 0) continue;

@@ -139,6 +139,33 @@ def test_random_scenes_bit_exact(seed):
         _assert_same(p, var, cam, tex, depth, w, h, what=f"seed {seed}")
 
 
+@pytest.mark.parametrize("variant", [(8, 0, abi.LIGHT_NONE, abi.SCATTER_V2), (32, 0, abi.LIGHT_NONE, abi.SCATTER_V2), (8, 32, abi.LIGHT_CHEAP, abi.SCATTER_V2),
+                                     (8, 16, abi.LIGHT_RAYMARCHED, abi.SCATTER_V2), (16, 32, abi.LIGHT_CHEAP, abi.SCATTER_V1)])
+def test_fp64_twin_bit_exact(variant):
+    """The oracle's T=double instantiation (the rounding-error bound quoted in every parity report) against the same
+    reference sources compiled with `float` = double (oracle/_ref/libatmo_ref64.so): LUT and frames, bit for bit."""
+    ns, nc, light, model = variant
+    w, h = 80, 45
+    p = scenes.demo_params()
+    if model == abi.SCATTER_V1:
+        p.density = 0.02
+    lut64 = O.bake_lut(p, dtype=np.float64)
+    assert np.array_equal(lut64.view(np.uint64), R.bake_lut(p, dtype=np.float64).view(np.uint64))
+    shape, cube, bn = Hh.demo_textures()
+    tex = O.Textures(lut=O.bake_lut(p), lut64=lut64, shape=shape, cube_faces=cube, blue_noise=bn)
+    for cam in (scenes.camera_a(w, h, orbit_deg=10.0), scenes.camera_b(w, h, p)):
+        depth = scenes.synth_depth(cam, p, w, h)
+        var = O.variant(ns, nc, light, model)
+        want, wdisc = R.render_frame(p, var, cam, tex, depth, w, h, dtype=np.float64)
+        got, gdisc = O.render_frame(p, var, cam, tex, depth, w, h, dtype=np.float64)
+        assert np.array_equal(gdisc, wdisc) and np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # and without a double LUT both sides widen the fp32 one
+    tex32 = O.Textures(lut=O.bake_lut(p), shape=shape, cube_faces=cube, blue_noise=bn)
+    want, _ = R.render_frame(p, var, cam, tex32, depth, w, h, dtype=np.float64)
+    got, _ = O.render_frame(p, var, cam, tex32, depth, w, h, dtype=np.float64)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
 def test_unset_textures_bit_exact():
     """README.md:46: unset samplers cover the atmosphere uniformly (white) — both sides agree, and no blue noise = no jitter."""
     w, h = 64, 36
@@ -175,7 +202,7 @@ def test_the_pin_has_teeth(tmp_path):
     rgba = np.zeros((h, w, 4), np.float32)
     disc = np.zeros((h, w), np.uint8)
     ts = tex.struct()
-    assert mlib.ref_render_frame_f32(None, C.byref(p), C.byref(var), C.byref(cam), C.byref(ts), O._ptr(np.ascontiguousarray(depth, np.float32)),
+    assert mlib.ref_render_frame(None, C.byref(p), C.byref(var), C.byref(cam), C.byref(ts), O._ptr(np.ascontiguousarray(depth, np.float32)),
                                      w, h, 0, h, 1, O._ptr(rgba), O._ptr(disc), 1) == 0
     got, _ = O.render_frame(p, var, cam, tex, depth, w, h)
     assert np.array_equal(_bits(got[..., :3]), _bits(rgba[..., :3]))          # colour untouched by the mutation

@@ -242,6 +242,9 @@ void PlanetAtmosphereB200::_bind_methods() {
     B200_PROP(godot::Variant::FLOAT, clouds_rotation_speed);
     B200_PROP(godot::Variant::BOOL, force_fullscreen);
 #undef B200_PROP
+    // the draw happens in a CompositorEffect: add it to the Compositor of the camera / WorldEnvironment that should show
+    // the atmosphere (the GDScript node added a MeshInstance3D child instead, planet_atmosphere.gd:84-103)
+    ClassDB::bind_method(D_METHOD("get_compositor_effect"), &PlanetAtmosphereB200::get_compositor_effect);
     ClassDB::bind_method(D_METHOD("set_shader_param", "param_name", "value"), &PlanetAtmosphereB200::set_shader_param);
     ClassDB::bind_method(D_METHOD("get_shader_param", "param_name"), &PlanetAtmosphereB200::get_shader_param);
     ClassDB::bind_method(D_METHOD("set_shader_parameter", "param_name", "value"), &PlanetAtmosphereB200::set_shader_parameter);
@@ -258,7 +261,7 @@ B200AtmosphereEffect::B200AtmosphereEffect() {
 
 void B200AtmosphereEffect::_render_callback(int32_t, RenderData* p_render_data) {
     if (!owner_ || !owner_->core() || !owner_->core()->ok()) return;
-    Ref<RenderSceneBuffersRD> buffers = p_render_data->get_render_scene_buffers();
+    Ref<RenderSceneBuffersRD> buffers = Object::cast_to<RenderSceneBuffersRD>(p_render_data->get_render_scene_buffers().ptr());
     RenderSceneData* scene = p_render_data->get_render_scene_data();
     RenderingDevice* rd = RenderingServer::get_singleton()->get_rendering_device();
     if (buffers.is_null() || !scene || !rd) return;

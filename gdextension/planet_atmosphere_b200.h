@@ -70,6 +70,7 @@ public:
     godot::PackedStringArray _get_configuration_warnings() const override;
 
     b200atmo::PlanetAtmosphere* core() { return core_.get(); }
+    godot::Ref<B200AtmosphereEffect> get_compositor_effect() const { return effect_; }
 
 protected:
     static void _bind_methods();

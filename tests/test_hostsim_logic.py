@@ -94,3 +94,38 @@ def test_magic_floor():
         x = float(np.float32(x))
         assert i + fr.value == pytest.approx(x, abs=1e-6) and -1e-6 <= fr.value <= 1.0 + 1e-6
         assert i in (int(np.floor(x)), int(np.floor(x)) - 1)
+
+
+@pytest.mark.parametrize("shader", ["planet_atmosphere_no_clouds", "planet_atmosphere_clouds_high", "planet_atmosphere_clouds_high_rm",
+                                    "planet_atmosphere_v1_clouds"])
+def test_device_logic_matches_the_compiled_reference(scene, shader):
+    """The product's device code (host build: front end + march) against oracle/_ref — the reference's own shader sources
+    compiled as C++ — on views the GPU tests do not all cover: far away, inside the cloud shell, underground, looking away."""
+    from godot_atmosphere_shader_b200.planet_atmosphere import SHADER_VARIANTS
+    from oracle import pyref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    p, hs, otex = scene
+    p = p.copy()
+    model, ns, nc, light = SHADER_VARIANTS[shader]
+    if model == abi.SCATTER_V1:
+        p.density = 0.02
+        lut = O.bake_lut(p)
+        shape, cube, bn = Hh.demo_textures()
+        hs = Hh.HostsimScene(lut, shape, cube, bn)
+        otex = O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+    w, h = 48, 27
+    R0, H0 = p.planet_radius, p.atmosphere_height
+    cams = [scenes.make_camera((0.0, 0.0, 1500.0), (0.0, 0.0, -1.0), aspect=w / h, far=4000.0),
+            scenes.make_camera((0.0, R0 + 0.4 * H0, 0.0), (1.0, -0.1, 0.2), aspect=w / h),
+            scenes.make_camera((0.0, R0 - 1.0, 0.0), (0.3, 1.0, 0.0), up=(0, 0, 1), aspect=w / h),
+            scenes.make_camera((0.0, 0.0, 157.0), (0.0, 0.2, 1.0), aspect=w / h),
+            scenes.camera_a(w, h, orbit_deg=75.0)]
+    var = O.variant(ns, nc, light, model)
+    for k, cam in enumerate(cams):
+        depth = scenes.synth_depth(cam, p, w, h)
+        od, dj, fr = hs.make_rays(p, cam, depth, w, h)
+        got, gdisc = hs.render_rays(p, var, fr, od, dj)
+        ref, rdisc = R.render_frame(p, var, cam, otex, depth, w, h, shader=shader)
+        assert np.array_equal(gdisc.reshape(h, w), rdisc), f"camera {k}"
+        Hh.assert_rgba_close(got.reshape(h, w, 4), ref, what=f"{shader} camera {k}")

@@ -491,8 +491,7 @@ static int frame_tables(b200atmo_ctx* ctx, const DevConsts& c, RayIO& io, cudaSt
     if (stale) {
         int rc = drain_slots(ctx);
         if (rc != B200ATMO_OK) return rc;
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
+        CU_TRY(ctx, cudaDeviceSynchronize());   // frames on ANY stream (also the caller's) may still read the old tables
         if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_ray_tables), &ctx->cap_ray_tables, need)) != B200ATMO_OK) return rc;
         ctx->tables_w = 0;
         CU_TRY(ctx, launch_ray_tables(c, ctx->d_ray_tables, ctx->d_ray_tables + c.fw, s));

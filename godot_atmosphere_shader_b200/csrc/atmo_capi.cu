@@ -128,6 +128,7 @@ int bake_if_stale(b200atmo_ctx* ctx, cudaStream_t s) {
     if (!ctx->lut_stale) return B200ATMO_OK;
     int drained = drain_slots(ctx);
     if (drained != B200ATMO_OK) return drained;
+    CU_TRY(ctx, cudaDeviceSynchronize());   // rare path: frames on any stream may still sample the old LUT
     CU_TRY(ctx, launch_bake_lut(ctx->params.planet_radius, ctx->params.atmosphere_height, ctx->params.density, ctx->d_lut,
                                 ctx->d_lut_pad, ctx->d_lut_cells, s));
     ctx->launches += 2;

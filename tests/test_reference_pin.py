@@ -207,3 +207,60 @@ def test_the_pin_has_teeth(tmp_path):
     got, _ = O.render_frame(p, var, cam, tex, depth, w, h)
     assert np.array_equal(_bits(got[..., :3]), _bits(rgba[..., :3]))          # colour untouched by the mutation
     assert (_bits(got[..., 3]) != _bits(rgba[..., 3])).mean() > 0.9            # alpha differs wherever jitter > 0
+
+
+@pytest.mark.skipif(not R.reference_present(), reason="needs the reference tree")
+def test_the_rewrite_is_syntax_only():
+    """Token audit of oracle/ref/build_ref.py: for every entry shader and the bake shader, the multiset of numeric
+    literals (values), identifiers and arithmetic operators of the rewritten text equals that of the original text, apart
+    from the keywords the rewrite is documented to add or drop. No constant, name or operator appears or disappears."""
+    import collections
+    import re
+
+    from oracle.ref import build_ref as B
+
+    def strip_comments(t):
+        t = re.sub(r"/\*.*?\*/", " ", t, flags=re.S)
+        return re.sub(r"//[^\n]*", " ", t)
+
+    tok = re.compile(r"[A-Za-z_]\w*|(?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?f?|0x[0-9a-fA-F]+|\d+u?|[-+*/<>=!?|^%\[\].&]")
+
+    def tokens(t):
+        out = collections.Counter()
+        for x in tok.findall(strip_comments(t)):
+            if re.fullmatch(r"(?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?f", x):
+                x = x[:-1]                      # the f suffix is syntax; the VALUE must be unchanged
+            out[x] += 1
+        return out
+
+    dropped_ok = {"uniform", "varying", "in", "out", "inout", "shader_type", "render_mode", "spatial", "canvas_item", "unshaded",
+                  "blend_disabled", "source_color", "repeat_disable", "repeat_enable", "filter_nearest", "hint_depth_texture",
+                  "discard", "ifdef", "endif", "DOUBLE_PRECISION", "height_curve"}
+    added_ok = {"static", "int", "define", "if", "true", "return", "ref_discarded", "ref_double_precision", "height_curve_value",
+                "ref_ATMOSPHERE_RAYMARCH_STEPS", "ref_CLOUDS_MAX_RAYMARCH_STEPS", "=", "&"}
+    files = [n + ".gdshader" for n in B.ENTRY_SHADERS] + ["optical_depth.gdshader"]
+    for f in files:
+        path = os.path.join(R.REFERENCE, B.SHADERS, f)
+        original = B.inline_includes(path, R.REFERENCE)
+        rewritten, _ = B.rewrite(original)
+        # inline_includes leaves '// >>> path' markers (comments) and removes the #include lines of the original files
+        raw = ""
+        seen = []
+
+        def gather(p):
+            for line in open(p, encoding="utf-8").read().splitlines():
+                m = re.match(r'\s*#include\s+"([^"]+)"', line)
+                if m:
+                    gather(os.path.normpath(os.path.join(os.path.dirname(p), m.group(1))))
+                else:
+                    seen.append(line)
+        gather(path)
+        raw = "\n".join(seen)
+        a, b = tokens(raw), tokens(rewritten)
+        gone = a - b
+        new = b - a
+        assert set(gone) <= dropped_ok, f"{f}: tokens lost by the rewrite: {sorted(set(gone) - dropped_ok)}"
+        assert set(new) <= added_ok, f"{f}: tokens introduced by the rewrite: {sorted(set(new) - added_ok)}"
+        # every numeric literal survives with its value and multiplicity
+        nums = lambda c: {k: v for k, v in c.items() if re.match(r"[\d.]", k) and k != "."}
+        assert nums(a) == nums(b), f"{f}: numeric literals changed"

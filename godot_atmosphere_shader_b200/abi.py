@@ -87,7 +87,8 @@ class B200AtmoPeerTargets(C.Structure):
     """Where the fused render + all-gather kernels store: the same symmetric buffer on every rank (include/b200atmo.h)."""
 
     _fields_ = [("d_rgba_peers", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32), ("d_rgba_multicast", C.c_void_p),
-                ("elem_offset", C.c_uint64), ("first_peer", C.c_int32), ("use_tma", C.c_int32)]
+                ("elem_offset", C.c_uint64), ("first_peer", C.c_int32), ("use_tma", C.c_int32), ("rgba_format", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class B200AtmoNoise(C.Structure):

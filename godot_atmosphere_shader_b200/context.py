@@ -25,7 +25,8 @@ EXPORTS = [
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
     "b200atmo_render_frame_host_submit", "b200atmo_frame_wait", "b200atmo_render_frame_composite_fmt", "b200atmo_composite_frame_host",
     "b200atmo_render_frame_peers", "b200atmo_render_rays_peers",
-    "b200atmo_launch_count",
+    "b200atmo_render_rays_2d", "b200atmo_render_frame_fmt", "b200atmo_render_frame_host_fmt", "b200atmo_render_frame_host_submit_fmt",
+    "b200atmo_launch_count", "b200atmo_table_build_count",
 ]
 
 
@@ -76,8 +77,13 @@ def lib():
         L.b200atmo_render_rays_peers.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, C.c_size_t, C.POINTER(abi.B200AtmoPeerTargets), vp]
         L.b200atmo_render_frame_composite_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp]
         L.b200atmo_composite_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32]
-        L.b200atmo_launch_count.argtypes = [vp]
-        L.b200atmo_launch_count.restype = C.c_uint64
+        L.b200atmo_render_rays_2d.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, i32, i32, vp, vp, vp]
+        L.b200atmo_render_frame_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp, vp]
+        L.b200atmo_render_frame_host_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32, vp]
+        L.b200atmo_render_frame_host_submit_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32, vp, i32]
+        for f in ("b200atmo_launch_count", "b200atmo_table_build_count"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = C.c_uint64
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = the library does not export what the header declares
         _lib = L
@@ -186,7 +192,15 @@ class AtmosphereContext:
         return buf
 
     # ---- rendering ----
-    def render_rays(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, rgba, discard=None, stream=None):
+    def render_rays(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, rgba, discard=None, stream=None, grid=None):
+        """`grid=(width, height)`: the batch is a row-major pixel grid (n == width*height) and warps are mapped to 8x4 tiles
+        (b200atmo_render_rays_2d); results are bit-identical to the linear mapping."""
+        if grid is not None:
+            w, h = int(grid[0]), int(grid[1])
+            assert w * h == int(n), "grid does not match the ray count"
+            self._check(lib().b200atmo_render_rays_2d(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), w, h,
+                                                      _dptr(rgba), _dptr(discard), stream))
+            return
         self._check(lib().b200atmo_render_rays(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
                                                _dptr(rgba), _dptr(discard), stream))
 
@@ -194,9 +208,12 @@ class AtmosphereContext:
         self._check(lib().b200atmo_render_rays_host(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
                                                     _dptr(rgba), _dptr(discard)))
 
-    def render_frame(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, row_begin=0, row_end=None, stream=None):
-        self._check(lib().b200atmo_render_frame(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
-                                                int(h if row_end is None else row_end), _dptr(rgba), _dptr(discard), stream))
+    def render_frame(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, row_begin=0, row_end=None, stream=None,
+                     rgba_format=COLOR_RGBA32F):
+        """`rgba_format=COLOR_RGBA16F`: rgba is half4 per pixel (the fp32 result rounded to nearest-even)."""
+        self._check(lib().b200atmo_render_frame_fmt(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
+                                                    int(h if row_end is None else row_end), _dptr(rgba), int(rgba_format),
+                                                    _dptr(discard), stream))
 
     def render_frame_composite(self, cam: B200AtmoCamera, depth, w, h, color_inout, row_begin=0, row_end=None, stream=None,
                                color_format=COLOR_RGBA32F):
@@ -216,9 +233,9 @@ class AtmosphereContext:
                                              _dptr(dir_jitter), C.byref(fr), stream))
         return fr
 
-    def render_frame_host(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None):
-        self._check(lib().b200atmo_render_frame_host(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
-                                                     _dptr(discard)))
+    def render_frame_host(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, rgba_format=COLOR_RGBA32F):
+        self._check(lib().b200atmo_render_frame_host_fmt(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
+                                                         int(rgba_format), _dptr(discard)))
 
     def render_frame_peers(self, cam: B200AtmoCamera, depth, w, h, targets, row_begin=0, row_end=None, stream=None):
         """Fused render + all-gather: rows [row_begin, row_end) go straight into every rank's symmetric buffer."""
@@ -229,10 +246,10 @@ class AtmosphereContext:
         self._check(lib().b200atmo_render_rays_peers(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
                                                      C.byref(targets), stream))
 
-    def render_frame_host_submit(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, slot=0):
+    def render_frame_host_submit(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, slot=0, rgba_format=COLOR_RGBA32F):
         """Pipelined host-buffer frame: returns after enqueueing; `frame_wait(slot)` completes it."""
-        self._check(lib().b200atmo_render_frame_host_submit(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
-                                                            _dptr(discard), int(slot)))
+        self._check(lib().b200atmo_render_frame_host_submit_fmt(self._h, C.byref(cam), _dptr(depth), int(w), int(h), _dptr(rgba),
+                                                                int(rgba_format), _dptr(discard), int(slot)))
 
     def frame_wait(self, slot=0):
         self._check(lib().b200atmo_frame_wait(self._h, int(slot)))
@@ -240,3 +257,7 @@ class AtmosphereContext:
     @property
     def launch_count(self) -> int:
         return int(lib().b200atmo_launch_count(self._h))
+
+    @property
+    def table_build_count(self) -> int:
+        return int(lib().b200atmo_table_build_count(self._h))

@@ -46,11 +46,26 @@ struct b200atmo_ctx {
         size_t cap_depth = 0, cap_rgba = 0, cap_disc = 0;
         bool in_flight = false;
     } slots[B200ATMO_PIPELINE_SLOTS];
-    // frame front end: per-column / per-row tables of INV_PROJECTION_MATRIX * ndc for the last (w, h, projection)
-    float4* d_ray_tables = nullptr;
-    size_t cap_ray_tables = 0;
-    int tables_w = 0, tables_h = 0;
-    float tables_inv_proj[16] = {};
+    // frame front end: per-column / per-row tables of INV_PROJECTION_MATRIX * ndc, cached PER STREAM (kTableStreams
+    // streams x kTableEntries (w, h, projection) keys, LRU). An entry is only ever built and read by work on its own
+    // stream, so builds are stream-ordered and no call ever synchronises: alternating viewports hit the cache, a
+    // projection that changes every frame (TAA jitter) costs one 2-us kernel per frame. Callers that use more streams
+    // than kTableStreams get the inline path (the kernel computes the same values per pixel: bit-identical).
+    static constexpr int kTableStreams = 16, kTableEntries = 4;
+    struct TableEntry {
+        float4* d = nullptr;
+        size_t cap = 0;
+        int w = 0, h = 0;
+        float inv_proj[16] = {};
+        uint64_t tick = 0;
+    };
+    struct TableStream {
+        cudaStream_t stream = nullptr;
+        bool used = false;
+        TableEntry e[kTableEntries];
+    } tables[kTableStreams];
+    uint64_t table_tick = 0;
+    uint64_t table_builds = 0;
     uint64_t launches = 0;
     std::string last_error;
 };
@@ -84,8 +99,6 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
-
-bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int ensure(b200atmo_ctx* ctx, void** p, size_t* cap, size_t need) {
     if (*cap >= need) return B200ATMO_OK;
@@ -291,7 +304,8 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
         cudaFree(sl.d_rgba);
         cudaFree(sl.d_disc);
     }
-    cudaFree(ctx->d_ray_tables);
+    for (auto& ts : ctx->tables)
+        for (auto& e : ts.e) cudaFree(e.d);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
     cudaFree(ctx->d_lut_cells);
@@ -345,8 +359,9 @@ int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps
 
 int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w, int h) {
     if (!ctx || !h_texels) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: NULL argument");
-    if (!is_pow2(w) || !is_pow2(h) || w > 4096 || h > 4096)
-        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: sizes must be powers of two <= 4096");
+    // main:168-169 fetches texel (x & 0xff, y & 0xff): the top-left 256 x 256 window of whatever is bound
+    if (w < 256 || h < 256 || w > 4096 || h > 4096)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_upload_blue_noise: sizes must be in [256, 4096] (the shader reads texel (x & 0xff, y & 0xff))");
     DeviceGuard g(ctx->device);
     DevBuf d;
     CU_TRY(ctx, d.alloc(size_t(w) * h));
@@ -418,8 +433,8 @@ int b200atmo_download_cube_padded(b200atmo_ctx* ctx, uint8_t* h_out, size_t cap,
     return B200ATMO_OK;
 }
 
-int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
-                         size_t n_rays, float* d_rgba, uint8_t* d_discard, void* stream) {
+static int render_rays_impl(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
+                            size_t n_rays, int width, int height, float* d_rgba, uint8_t* d_discard, void* stream) {
     if (!ctx || !frame) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays: NULL ctx/frame");
     if (n_rays == 0) return B200ATMO_OK;
     if (!d_origin_depth || !d_dir_jitter || !d_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays: NULL buffer");
@@ -431,6 +446,8 @@ int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const fl
     DevConsts c;
     consts_from_params(c, ctx->params, ctx->variant, textures_of(ctx));
     consts_set_frame(c, ctx->params, frame->planet_center_view, frame->sun_center_view, frame->inv_view);
+    c.fw = width;    // > 0: the batch is a width x height pixel grid, warps cover 8x4 tiles (launch_rays_t)
+    c.fh = height;
     RayIO io{};
     io.origin_depth = d_origin_depth;
     io.dir_jitter = d_dir_jitter;
@@ -440,6 +457,18 @@ int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const fl
     CU_TRY(ctx, launch_render_rays(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
+}
+
+int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
+                         size_t n_rays, float* d_rgba, uint8_t* d_discard, void* stream) {
+    return render_rays_impl(ctx, frame, d_origin_depth, d_dir_jitter, n_rays, 0, 0, d_rgba, d_discard, stream);
+}
+
+int b200atmo_render_rays_2d(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
+                            int width, int height, float* d_rgba, uint8_t* d_discard, void* stream) {
+    if (width < 0 || height < 0) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_rays_2d: negative size");
+    return render_rays_impl(ctx, frame, d_origin_depth, d_dir_jitter, size_t(width) * size_t(height), width, height, d_rgba, d_discard,
+                            stream);
 }
 
 int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* h_origin_depth,
@@ -483,33 +512,69 @@ static int frame_consts(b200atmo_ctx* ctx, const B200AtmoCamera* cam, int w, int
     return B200ATMO_OK;
 }
 
-// Per-column / per-row tables of the frame front end (make_ray): rebuilt only when the frame size or the projection
-// changes (rare: resize, FOV change), then shared by every stream — hence the drain + synchronise on that path.
+// Per-column / per-row tables of the frame front end (make_ray), from the per-stream cache (see b200atmo_ctx::tables).
+// Never synchronises: a miss allocates (first use of an entry, or a larger frame) and launches ray_tables_kernel on `s`,
+// ahead of the frame kernel that reads it on the same stream.
 static int frame_tables(b200atmo_ctx* ctx, const DevConsts& c, RayIO& io, cudaStream_t s) {
-    const size_t need = size_t(c.fw + c.fh) * sizeof(float4);
-    const bool stale = ctx->tables_w != c.fw || ctx->tables_h != c.fh ||
-                       std::memcmp(ctx->tables_inv_proj, c.inv_proj, sizeof(ctx->tables_inv_proj)) != 0;
-    if (stale) {
-        int rc = drain_slots(ctx);
-        if (rc != B200ATMO_OK) return rc;
-        CU_TRY(ctx, cudaDeviceSynchronize());   // frames on ANY stream (also the caller's) may still read the old tables
-        if ((rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_ray_tables), &ctx->cap_ray_tables, need)) != B200ATMO_OK) return rc;
-        ctx->tables_w = 0;
-        CU_TRY(ctx, launch_ray_tables(c, ctx->d_ray_tables, ctx->d_ray_tables + c.fw, s));
-        ctx->launches++;
-        CU_TRY(ctx, cudaStreamSynchronize(s));
-        ctx->tables_w = c.fw;
-        ctx->tables_h = c.fh;
-        std::memcpy(ctx->tables_inv_proj, c.inv_proj, sizeof(ctx->tables_inv_proj));
+    b200atmo_ctx::TableStream* ts = nullptr;
+    for (auto& t : ctx->tables)
+        if (t.used && t.stream == s) { ts = &t; break; }
+    if (!ts)
+        for (auto& t : ctx->tables)
+            if (!t.used) { ts = &t; t.used = true; t.stream = s; break; }
+    if (!ts) {   // more caller streams than cache rows: inline path (same arithmetic per pixel)
+        io.ray_col = nullptr;
+        io.ray_row = nullptr;
+        return B200ATMO_OK;
     }
-    io.ray_col = ctx->d_ray_tables;
-    io.ray_row = ctx->d_ray_tables + c.fw;
+    b200atmo_ctx::TableEntry* hit = nullptr;
+    b200atmo_ctx::TableEntry* lru = &ts->e[0];
+    for (auto& e : ts->e) {
+        if (e.d && e.w == c.fw && e.h == c.fh && std::memcmp(e.inv_proj, c.inv_proj, sizeof(e.inv_proj)) == 0) { hit = &e; break; }
+        if (e.tick < lru->tick) lru = &e;
+    }
+    if (!hit) {
+        const size_t need = size_t(c.fw + c.fh) * sizeof(float4);
+        if (lru->cap < need) {
+            // stream-ordered free + allocate: kernels already queued on `s` may still read the old buffer
+            if (lru->d) CU_TRY(ctx, cudaFreeAsync(lru->d, s));
+            lru->d = nullptr;
+            lru->cap = 0;
+            CU_TRY(ctx, cudaMallocAsync(reinterpret_cast<void**>(&lru->d), need, s));
+            lru->cap = need;
+        }
+        lru->w = 0;
+        CU_TRY(ctx, launch_ray_tables(c, lru->d, lru->d + c.fw, s));
+        ctx->launches++;
+        ctx->table_builds++;
+        lru->w = c.fw;
+        lru->h = c.fh;
+        std::memcpy(lru->inv_proj, c.inv_proj, sizeof(lru->inv_proj));
+        hit = lru;
+    }
+    hit->tick = ++ctx->table_tick;
+    io.ray_col = hit->d;
+    io.ray_row = hit->d + c.fw;
     return B200ATMO_OK;
 }
 
-int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
-                          int row_end, float* d_rgba, uint8_t* d_discard, void* stream) {
+static bool valid_format(int f) { return f == B200ATMO_COLOR_RGBA32F || f == B200ATMO_COLOR_RGBA16F; }
+static size_t format_bytes(int f) { return f == B200ATMO_COLOR_RGBA16F ? 8 : 16; }
+
+// one frame-kernel launch for rows [c.row_begin, c.row_end) in either result format
+static cudaError_t launch_frame_any(const DevConsts& c, const RayIO& io, int rgba_format, const Variant& v, cudaStream_t s) {
+    if (rgba_format == B200ATMO_COLOR_RGBA16F && !io.color_inout) {
+        RayIO16 io16;
+        static_cast<RayIO&>(io16) = io;
+        return launch_render_frame16(c, io16, v.scatter_model, v.light_mode, s);
+    }
+    return launch_render_frame(c, io, v.scatter_model, v.light_mode, s);
+}
+
+int b200atmo_render_frame_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                              int row_end, void* d_rgba, int rgba_format, uint8_t* d_discard, void* stream) {
     if (!ctx || !cam || !d_depth || !d_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame: NULL argument");
+    if (!valid_format(rgba_format)) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame: unknown result format");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DevConsts c;
@@ -523,9 +588,14 @@ int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const fl
     io.discard = d_discard;
     io.n = size_t(w) * h;
     if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
-    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+    CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, s));
     ctx->launches++;
     return B200ATMO_OK;
+}
+
+int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                          int row_end, float* d_rgba, uint8_t* d_discard, void* stream) {
+    return b200atmo_render_frame_fmt(ctx, cam, d_depth, w, h, row_begin, row_end, d_rgba, B200ATMO_COLOR_RGBA32F, d_discard, stream);
 }
 
 int b200atmo_render_frame_composite_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
@@ -580,7 +650,6 @@ int b200atmo_composite_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, 
     io.color_inout = d_color;
     io.color_format = color_format;
     io.n = npx;
-    if ((rc = frame_tables(ctx, c, io, ctx->streams[0])) != B200ATMO_OK) return rc;
     // equal row bands alternating over two streams: the uploads of band k+1 (12 or 20 B/pixel) run while band k downloads
     // (8 or 16 B/pixel); PCIe is full duplex, so the slower direction bounds the frame
     const int bands = h >= 512 ? 8 : (h >= 256 ? 4 : 1);   // the upload is the longer leg here: finer bands shorten the tail
@@ -593,6 +662,7 @@ int b200atmo_composite_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, 
         CU_TRY(ctx, cudaMemcpyAsync(d_color + off * px_bytes, h_color + off * px_bytes, cnt * px_bytes, cudaMemcpyHostToDevice, s));
         c.row_begin = r0;
         c.row_end = r1;
+        if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;   // per-stream cache: each band stream has its own copy
         CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
         ctx->launches++;
         CU_TRY(ctx, cudaMemcpyAsync(h_color + off * px_bytes, d_color + off * px_bytes, cnt * px_bytes, cudaMemcpyDeviceToHost, s));
@@ -634,19 +704,21 @@ int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float
     return B200ATMO_OK;
 }
 
-int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h, float* h_rgba,
-                               uint8_t* h_discard) {
+int b200atmo_render_frame_host_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h, void* h_rgba,
+                                   int rgba_format, uint8_t* h_discard) {
     if (!ctx || !cam || !h_depth || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host: NULL argument");
     if (w < 1 || h < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host: bad size");
+    if (!valid_format(rgba_format)) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host: unknown result format");
     DeviceGuard g(ctx->device);
-    const size_t npx = size_t(w) * h;
+    const size_t npx = size_t(w) * h, pxb = format_bytes(rgba_format);
     int rc;
     if ((rc = ensure(ctx, &ctx->d_stage_in0, &ctx->cap_in0, npx * sizeof(float))) != B200ATMO_OK) return rc;
-    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, npx * 4 * sizeof(float))) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->cap_out, npx * pxb)) != B200ATMO_OK) return rc;
     if (h_discard && (rc = ensure(ctx, reinterpret_cast<void**>(&ctx->d_stage_disc), &ctx->cap_disc, npx)) != B200ATMO_OK) return rc;
     if ((rc = bake_if_stale(ctx, ctx->streams[0])) != B200ATMO_OK) return rc;
     float* d_depth = static_cast<float*>(ctx->d_stage_in0);
-    float* d_rgba = static_cast<float*>(ctx->d_stage_out);
+    char* d_rgba = static_cast<char*>(ctx->d_stage_out);
+    char* h_out = static_cast<char*>(h_rgba);
     DevConsts c;
     if ((rc = frame_consts(ctx, cam, w, h, 0, h, c)) != B200ATMO_OK) return rc;
     RayIO io{};
@@ -654,9 +726,8 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
     io.rgba = d_rgba;
     io.discard = h_discard ? ctx->d_stage_disc : nullptr;
     io.n = npx;
-    if ((rc = frame_tables(ctx, c, io, ctx->streams[0])) != B200ATMO_OK) return rc;
-    // Row bands, alternating over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band). The D2H of 16 B/px
-    // is the PCIe-bound leg (4x the H2D), so the first band is small (the D2H engine starts early) and bands grow by
+    // Row bands, alternating over two streams: H2D(depth band) -> kernel(band) -> D2H(rgba band). The D2H (16 or 8 B/px)
+    // is the PCIe-bound leg, so the first band is small (the D2H engine starts early) and bands grow by
     // ~1.5x: each band's upload + kernel hides behind the previous band's download. Few bands: the host issues
     // ~3 API calls per band at ~5 us each.
     int bands = h >= 256 ? 4 : 1;   // measured on B200: 3-5 bands are equivalent (0.72-0.75 ms at 1080p, PCIe floor 0.61 ms)
@@ -678,15 +749,21 @@ int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, con
         CU_TRY(ctx, cudaMemcpyAsync(d_depth + off, h_depth + off, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
         c.row_begin = r0;
         c.row_end = r1;
-        CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
+        if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;   // per-stream cache: each band stream has its own copy
+        CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, s));
         ctx->launches++;
-        CU_TRY(ctx, cudaMemcpyAsync(h_rgba + 4 * off, d_rgba + 4 * off, cnt * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU_TRY(ctx, cudaMemcpyAsync(h_out + off * pxb, d_rgba + off * pxb, cnt * pxb, cudaMemcpyDeviceToHost, s));
         if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard + off, ctx->d_stage_disc + off, cnt, cudaMemcpyDeviceToHost, s));
         r0 = r1;
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[0]));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[1]));
     return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h, float* h_rgba,
+                               uint8_t* h_discard) {
+    return b200atmo_render_frame_host_fmt(ctx, cam, h_depth, w, h, h_rgba, B200ATMO_COLOR_RGBA32F, h_discard);
 }
 
 static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPeers& io, const char* who) {
@@ -701,6 +778,8 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     io.use_tma = t->use_tma != 0;
     io.rgba_multicast = t->d_rgba_multicast;
     io.peer_offset = size_t(t->elem_offset);
+    if (!valid_format(t->rgba_format)) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": unknown tile format");
+    io.rgba_half = t->rgba_format == B200ATMO_COLOR_RGBA16F ? 1 : 0;
     return B200ATMO_OK;
 }
 
@@ -747,18 +826,19 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
     return B200ATMO_OK;
 }
 
-int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
-                                      float* h_rgba, uint8_t* h_discard, int slot) {
+int b200atmo_render_frame_host_submit_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
+                                          void* h_rgba, int rgba_format, uint8_t* h_discard, int slot) {
     if (!ctx || !cam || !h_depth || !h_rgba) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: NULL argument");
     if (w < 1 || h < 1) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: bad size");
+    if (!valid_format(rgba_format)) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: unknown result format");
     if (slot < 0 || slot >= B200ATMO_PIPELINE_SLOTS) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_host_submit: bad slot");
     b200atmo_ctx::Slot& sl = ctx->slots[slot];
     if (sl.in_flight) return fail(ctx, B200ATMO_E_STATE, "b200atmo_render_frame_host_submit: slot still in flight (call b200atmo_frame_wait)");
     DeviceGuard g(ctx->device);
-    const size_t npx = size_t(w) * h;
+    const size_t npx = size_t(w) * h, pxb = format_bytes(rgba_format);
     int rc;
     if ((rc = ensure(ctx, &sl.d_depth, &sl.cap_depth, npx * sizeof(float))) != B200ATMO_OK) return rc;
-    if ((rc = ensure(ctx, &sl.d_rgba, &sl.cap_rgba, npx * 4 * sizeof(float))) != B200ATMO_OK) return rc;
+    if ((rc = ensure(ctx, &sl.d_rgba, &sl.cap_rgba, npx * pxb)) != B200ATMO_OK) return rc;
     if (h_discard && (rc = ensure(ctx, &sl.d_disc, &sl.cap_disc, npx)) != B200ATMO_OK) return rc;
     if ((rc = bake_if_stale(ctx, sl.stream)) != B200ATMO_OK) return rc;
     DevConsts c;   // uniforms, variant and camera are captured here (kernel parameter space)
@@ -771,11 +851,16 @@ int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* c
     if ((rc = frame_tables(ctx, c, io, sl.stream)) != B200ATMO_OK) return rc;
     sl.in_flight = true;   // from the first enqueue on the host buffers are in use, also if a later enqueue fails
     CU_TRY(ctx, cudaMemcpyAsync(sl.d_depth, h_depth, npx * sizeof(float), cudaMemcpyHostToDevice, sl.stream));
-    CU_TRY(ctx, launch_render_frame(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, sl.stream));
+    CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, sl.stream));
     ctx->launches++;
-    CU_TRY(ctx, cudaMemcpyAsync(h_rgba, sl.d_rgba, npx * 4 * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    CU_TRY(ctx, cudaMemcpyAsync(h_rgba, sl.d_rgba, npx * pxb, cudaMemcpyDeviceToHost, sl.stream));
     if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard, sl.d_disc, npx, cudaMemcpyDeviceToHost, sl.stream));
     return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth, int w, int h,
+                                      float* h_rgba, uint8_t* h_discard, int slot) {
+    return b200atmo_render_frame_host_submit_fmt(ctx, cam, h_depth, w, h, h_rgba, B200ATMO_COLOR_RGBA32F, h_discard, slot);
 }
 
 int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot) {
@@ -790,5 +875,6 @@ int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot) {
 }
 
 uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t b200atmo_table_build_count(const b200atmo_ctx* ctx) { return ctx ? ctx->table_builds : 0; }
 
 }  // extern "C"

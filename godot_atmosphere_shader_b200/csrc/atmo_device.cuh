@@ -661,7 +661,9 @@ B200_DEV void make_ray(const DevConsts& c, int x, int y, float nonlinear_depth, 
     const float l = sqrtf(dot3(v, v));
     d = mk3(v.x / l, v.y / l, v.z / l);                                                   // :142
     jitter = 0.0f;
-    if (c.blue_noise) jitter = float(c.blue_noise[(y & (c.bn_h - 1)) * c.bn_w + (x & (c.bn_w - 1))]) / 255.0f;  // :168-169
+    // :168-169: texelFetch(u_blue_noise_texture, ivec2(px) & ivec2(0xff), 0) — a FIXED 256x256 window whatever the texture
+    // size (uploads smaller than 256 are rejected: the shader would fetch out of range)
+    if (c.blue_noise) jitter = float(c.blue_noise[(y & 0xff) * c.bn_w + (x & 0xff)]) / 255.0f;
 }
 
 }  // namespace b200atmo

@@ -81,6 +81,9 @@ struct RayIO {
     const float4* ray_col;     // [fw]  m[0..3] * ndc.x(x)
     const float4* ray_row;     // [fh]  m[4..7] * ndc.y(y)
 };
+// RGBA16F result (b200atmo_render_frame*_fmt): the same fields, a different TYPE, so the store is chosen at compile time and
+// the fp32 kernels keep their code byte for byte. rgba = half4[...].
+struct RayIO16 : RayIO {};
 // fused render + all-gather (b200atmo_render_*_peers): the result goes to the same symmetric buffer on every GPU instead
 // of `rgba`: one multimem store when the NVLS multicast mapping is given, else one P2P store per peer. A separate
 // parameter type, so the single-GPU kernels keep exactly the code (and parameter layout) they have without this path.
@@ -90,7 +93,8 @@ struct RayIOPeers : RayIO {
     int n_peers;
     int first_peer;            // store loop starts here and wraps (ranks stagger their destinations)
     int use_tma;               // ray kernel: stage the block's results in smem, one cp.async.bulk per peer
-    size_t peer_offset;        // float4 elements added to the pixel / ray index in the peer buffers
+    size_t peer_offset;        // pixels (float4 or half4 elements) added to the pixel / ray index in the peer buffers
+    int rgba_half;             // tile format on the wire: 0 = float4, 1 = half4 (RTN-even of the fp32 result)
 };
 
 #ifdef __CUDACC__
@@ -103,6 +107,7 @@ cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_
 cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s);
+cudaError_t launch_render_frame16(const DevConsts& c, const RayIO16& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
 cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, cudaStream_t s);
 #endif

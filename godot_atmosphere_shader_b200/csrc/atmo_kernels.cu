@@ -207,8 +207,32 @@ constexpr int kBlock = B200ATMO_BLOCK;
 // second pass over the tile); without it, one peer-to-peer store per rank.
 // Overloaded on the parameter type (RayIOPeers only for the *_peers kernels): the single-GPU kernels compile to
 // exactly the code they have without this path.
+// RGBA16F: every channel rounded to nearest-even, like a store into an RGBA16F colour target
+__device__ __forceinline__ uint2 pack_half4(float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+}
 __device__ __forceinline__ void store_rgba(const RayIO& io, size_t i, float4 v) { __stcs(static_cast<float4*>(io.rgba) + i, v); }
+__device__ __forceinline__ void store_rgba(const RayIO16& io, size_t i, float4 v) {
+    const uint2 h = pack_half4(v);
+    __stcs(reinterpret_cast<float2*>(io.rgba) + i, make_float2(__uint_as_float(h.x), __uint_as_float(h.y)));
+}
 __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float4 v) {
+    if (io.rgba_half) {   // half4 tiles: 8 bytes per pixel on the wire
+        const uint2 h = pack_half4(v);
+        if (io.rgba_multicast) {
+            uint2* p = static_cast<uint2*>(io.rgba_multicast) + io.peer_offset + i;
+            asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__uint_as_float(h.x)), "f"(__uint_as_float(h.y))
+                         : "memory");
+        } else {
+            int r = io.first_peer;
+            for (int k = 0; k < io.n_peers; ++k) {
+                static_cast<uint2*>(io.rgba_peers[r])[io.peer_offset + i] = h;
+                r = (r + 1 == io.n_peers) ? 0 : r + 1;
+            }
+        }
+        return;
+    }
     if (io.rgba_multicast) {
         float4* p = static_cast<float4*>(io.rgba_multicast) + io.peer_offset + i;
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -223,10 +247,22 @@ __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float
 }
 
 // Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
-template <int MODEL, int LIGHT, class IO>
+// TILED (b200atmo_render_rays_2d): the batch is a c.fw x c.fh pixel grid; a warp covers an 8x4 pixel tile like the frame
+// kernel (four 128-byte segments per load instead of one 512-byte run), so its lanes enter and leave the cloud shell
+// together. A separate instantiation: the linear kernel keeps its code byte for byte.
+template <int MODEL, int LIGHT, class IO, bool TILED>
 __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const IO io) {
-    const size_t i = blockIdx.x * size_t(kBlock) + threadIdx.x;
-    if (i >= io.n) return;
+    size_t i;
+    if (TILED) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+        const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+        if (x >= c.fw || y >= c.fh) return;
+        i = size_t(y) * c.fw + x;
+    } else {
+        i = blockIdx.x * size_t(kBlock) + threadIdx.x;
+        if (i >= io.n) return;
+    }
     const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
     const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
     float4 out;
@@ -240,7 +276,7 @@ __global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevCo
 // peer mapping), instead of 128 threads x n_peers STG.128. No thread leaves before the barrier.
 template <int MODEL, int LIGHT>
 __global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_constant__ DevConsts c, const RayIOPeers io) {
-    __shared__ __align__(128) float4 s_out[kBlock];
+    __shared__ __align__(128) float4 s_out[kBlock];   // half4 tiles use the first half of it
     const size_t base = blockIdx.x * size_t(kBlock);
     const size_t i = base + threadIdx.x;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -249,16 +285,18 @@ __global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_consta
         const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
         shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
     }
-    s_out[threadIdx.x] = out;
+    const unsigned px_bytes = io.rgba_half ? 8u : 16u;
+    if (io.rgba_half) reinterpret_cast<uint2*>(s_out)[threadIdx.x] = pack_half4(out);
+    else s_out[threadIdx.x] = out;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async (TMA) proxy
     __syncthreads();
     if (threadIdx.x == 0) {
         const size_t left = io.n - base;
-        const unsigned bytes = unsigned(left < size_t(kBlock) ? left : size_t(kBlock)) * 16u;
+        const unsigned bytes = unsigned(left < size_t(kBlock) ? left : size_t(kBlock)) * px_bytes;
         const unsigned src = unsigned(__cvta_generic_to_shared(s_out));
         int r = io.first_peer;
         for (int k = 0; k < io.n_peers; ++k) {
-            float4* dst = static_cast<float4*>(io.rgba_peers[r]) + io.peer_offset + base;
+            char* dst = static_cast<char*>(io.rgba_peers[r]) + (io.peer_offset + base) * px_bytes;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
             r = (r + 1 == io.n_peers) ? 0 : r + 1;
         }
@@ -331,37 +369,44 @@ cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, 
     return cudaGetLastError();
 }
 
-#define B200ATMO_DISPATCH(KERNEL, IO, GRID, ...)                                                              \
+// KERNEL<MODEL, LIGHT, TAIL...>: TAIL = the remaining template arguments (IO type [, TILED])
+#define B200ATMO_DISPATCH(KERNEL, GRID, TAIL, ...)                                                            \
     do {                                                                                                     \
         if (scatter_model == B200ATMO_SCATTER_V1) {                                                           \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);     \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<1, 2, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                       \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);   \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<1, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                     \
         } else {                                                                                             \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);     \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<0, 2, IO><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                       \
+            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);   \
+            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
+            else KERNEL<0, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                     \
         }                                                                                                    \
     } while (0)
+#define B200ATMO_COMMA ,
 
 template <class IO> static cudaError_t launch_rays_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     if (io.n == 0) return cudaSuccess;
-    const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
-    B200ATMO_DISPATCH(render_rays_kernel, IO, grid, c, io);
+    if (c.fw > 0) {   // 2D batch: 16x8 pixel tile per block
+        const dim3 grid((c.fw + 15) / 16, (c.fh + 7) / 8);
+        B200ATMO_DISPATCH(render_rays_kernel, grid, IO B200ATMO_COMMA true, c, io);
+    } else {
+        const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
+        B200ATMO_DISPATCH(render_rays_kernel, grid, IO B200ATMO_COMMA false, c, io);
+    }
     return cudaGetLastError();
 }
 template <class IO> static cudaError_t launch_frame_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     const int rows = c.row_end - c.row_begin;
     if (rows <= 0 || c.fw <= 0) return cudaSuccess;
     const dim3 grid((c.fw + 15) / 16, (rows + 7) / 8);
-    B200ATMO_DISPATCH(render_frame_kernel, IO, grid, c, io);
+    B200ATMO_DISPATCH(render_frame_kernel, grid, IO, c, io);
     return cudaGetLastError();
 }
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
     return launch_rays_t(c, io, scatter_model, light_mode, s);
 }
 cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s) {
-    if (!io.use_tma || io.rgba_multicast) return launch_rays_t(c, io, scatter_model, light_mode, s);
+    if (!io.use_tma || io.rgba_multicast || c.fw > 0) return launch_rays_t(c, io, scatter_model, light_mode, s);   // the TMA kernel stages LINEAR runs of 128 results
     if (io.n == 0) return cudaSuccess;
     const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
     if (scatter_model == B200ATMO_SCATTER_V1) {
@@ -376,6 +421,9 @@ cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, i
     return cudaGetLastError();
 }
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
+    return launch_frame_t(c, io, scatter_model, light_mode, s);
+}
+cudaError_t launch_render_frame16(const DevConsts& c, const RayIO16& io, int scatter_model, int light_mode, cudaStream_t s) {
     return launch_frame_t(c, io, scatter_model, light_mode, s);
 }
 cudaError_t launch_render_frame_peers(const DevConsts& c, const RayIOPeers& io, int scatter_model, int light_mode, cudaStream_t s) {

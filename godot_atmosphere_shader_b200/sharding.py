@@ -86,7 +86,8 @@ def render_tile_and_gather_overlapped(ctx, cam, d_depth, width: int, height: int
 # ------------------------------------------------------------------------------------------------
 # fused render + all-gather over NVLink / NVSwitch peer memory (b200atmo_render_*_peers)
 # ------------------------------------------------------------------------------------------------
-def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_peer: int = 0, use_tma: bool = False):
+def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_peer: int = 0, use_tma: bool = False,
+                 rgba_format: int = 0):
     """B200AtmoPeerTargets from the device addresses of one symmetric buffer as mapped in this process."""
     from .abi import MAX_PEERS, B200AtmoPeerTargets
 
@@ -103,6 +104,7 @@ def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_pe
     t.elem_offset = int(elem_offset)
     t.first_peer = int(first_peer) % len(ptrs)   # (rank + 1) % world staggers the ranks' destinations
     t.use_tma = 1 if use_tma else 0
+    t.rgba_format = int(rgba_format)
     return t
 
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200ATMO_VERSION 1
+#define B200ATMO_VERSION 2
 
 enum {
     B200ATMO_OK = 0,
@@ -147,8 +147,9 @@ int b200atmo_get_params(const b200atmo_ctx* ctx, B200AtmoParams* out);
 int b200atmo_set_variant(b200atmo_ctx* ctx, int scatter_model, int scatter_steps, int cloud_steps, int light_mode);
 
 /* ---- textures (host -> device; the context keeps its own device copy) -------------------------- */
-/* u_blue_noise_texture (planet_atmosphere_main.gdshaderinc:63,168-169): w x h, 8-bit, nearest, repeat.
- * Sizes must be powers of two in [1, 4096] for the `& 0xff`-style wrap; the reference uses 256 x 256. */
+/* u_blue_noise_texture (planet_atmosphere_main.gdshaderinc:63,168-169): w x h, 8-bit. The shader fetches
+ * texelFetch(tex, ivec2(pixel) & ivec2(0xff), 0): always the top-left 256 x 256 texels, whatever the texture size, so
+ * 256 <= w, h <= 4096 is required (a smaller texture would be fetched out of range); the reference ships 256 x 256. */
 int b200atmo_upload_blue_noise(b200atmo_ctx* ctx, const uint8_t* h_texels, int w, int h);
 /* u_cloud_shape_texture (cloud_funcs.gdshaderinc:10,48-50): nx*ny*nz 8-bit, x fastest; trilinear, repeat. */
 int b200atmo_upload_shape3d(b200atmo_ctx* ctx, const uint8_t* h_texels, int nx, int ny, int nz);
@@ -195,6 +196,13 @@ int b200atmo_download_cube_padded(b200atmo_ctx* ctx, uint8_t* h_out, size_t cap,
 int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
                          const float* d_origin_depth, const float* d_dir_jitter, size_t n_rays,
                          float* d_rgba, uint8_t* d_discard, void* stream);
+/* The same call for a ray batch that is a width x height pixel grid in row-major order (n_rays = width*height): warps are
+ * mapped to 8x4 pixel tiles instead of 32 consecutive rays, so the lanes of a warp enter / leave the cloud shell together
+ * (lane-occupancy model profiles/r02/warp_model.txt: 8-15 % fewer issued instructions on the cloud variants). Results
+ * are bit-identical to b200atmo_render_rays. */
+int b200atmo_render_rays_2d(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
+                            const float* d_origin_depth, const float* d_dir_jitter, int width, int height,
+                            float* d_rgba, uint8_t* d_discard, void* stream);
 /* Same call with HOST buffers: H2D of the rays, render, D2H of the result; synchronous. */
 int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
                               const float* h_origin_depth, const float* h_dir_jitter, size_t n_rays,
@@ -240,6 +248,16 @@ int b200atmo_make_rays(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float
 int b200atmo_render_frame_host(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
                                int w, int h, float* h_rgba, uint8_t* h_discard);
 
+/* Output-format variants of the two host-buffer frame calls. B200ATMO_COLOR_RGBA16F writes h_rgba as w*h half4 (8 B/pixel
+ * instead of 16): every channel is the fp32 result rounded to nearest-even, (0,0,0,0) when discarded — i.e. exactly what
+ * storing ALBEDO/ALPHA into Godot's RGBA16F colour target does. The D2H of the result is the PCIe-bound leg of a host frame,
+ * so this halves the end-to-end time; the fp32 format stays the parity path. */
+int b200atmo_render_frame_host_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
+                                   int w, int h, void* h_rgba, int rgba_format, uint8_t* h_discard);
+/* Device-buffer frame call with an output format (rows [row_begin,row_end) of d_rgba: float4 or half4 per pixel). */
+int b200atmo_render_frame_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                              int row_end, void* d_rgba, int rgba_format, uint8_t* d_discard, void* stream);
+
 /* ---- multi-GPU: fused render + all-gather over NVLink / NVSwitch peer memory ---------------------------------- */
 /*
  * The screen-tile shard (one process per GPU, rank g renders rows [g*H/G, (g+1)*H/G) or its own tile) ends with every
@@ -261,7 +279,14 @@ typedef struct B200AtmoPeerTargets {
     int32_t use_tma;                        /* b200atmo_render_rays_peers, P2P path: != 0 stages each block's 128 results in shared
                                                memory and sends them with one TMA bulk store (cp.async.bulk) per peer instead of one
                                                STG.128 per thread and peer. Needs 16-byte aligned buffers and elem_offset. */
+    int32_t rgba_format;                    /* B200ATMO_COLOR_RGBA32F (float4 per pixel) or B200ATMO_COLOR_RGBA16F (half4 per pixel,
+                                               each channel the fp32 result rounded to nearest-even): the tile format on the wire.
+                                               Half the NVLink bytes; elem_offset counts pixels of that format. */
+    int32_t reserved;
 } B200AtmoPeerTargets;
+/* Delivery patterns are chosen by the pointer list alone: all ranks' mappings = all-gather (every GPU ends with every
+ * tile); ONLY the consuming rank's mapping (n_peers = 1) = deliver-to-root (1/world of the fabric traffic of the
+ * all-gather; the root's NVLink ingress is then the only loaded port). */
 int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
                                 int row_begin, int row_end, const B200AtmoPeerTargets* targets, void* stream);
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth,
@@ -280,10 +305,15 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
 #define B200ATMO_PIPELINE_SLOTS 2
 int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
                                       int w, int h, float* h_rgba, uint8_t* h_discard, int slot);
+int b200atmo_render_frame_host_submit_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
+                                          int w, int h, void* h_rgba, int rgba_format, uint8_t* h_discard, int slot);
 int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot);
 
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches claim). */
 uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx);
+/* Number of times the frame front end rebuilt its per-column / per-row ray tables (a cache keyed by stream, frame size and
+ * projection; alternating viewports must not rebuild, and no frame call ever synchronises the device for them). */
+uint64_t b200atmo_table_build_count(const b200atmo_ctx* ctx);
 
 #ifdef __cplusplus
 }

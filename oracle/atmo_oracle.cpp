@@ -128,10 +128,10 @@ void render_frame(const B200AtmoParams* p, const OracleVariant* v, const B200Atm
             vec3<T> o, d;
             T linear_depth;
             fragment_make_ray(inv_proj, inv_view, dp, T(depth[i]), su, sv, &o, &d, &linear_depth);
-            // main:168-169: ivec2(viewport_size*screen_uv) & 0xff  ->  (x, y) & (size-1); nearest, repeat
+            // main:168-169: texelFetch(tex, ivec2(viewport_size*screen_uv) & ivec2(0xff), 0): a fixed 256x256 window (bn_w, bn_h >= 256)
             T jitter = T(0);
             if (tex && tex->blue_noise)
-                jitter = T(tex->blue_noise[size_t(y & (tex->bn_h - 1)) * tex->bn_w + (x & (tex->bn_w - 1))]) / T(255);
+                jitter = T(tex->blue_noise[size_t(y & 0xff) * tex->bn_w + (x & 0xff)]) / T(255);
             vec3<T> albedo = {T(0), T(0), T(0)};
             T alpha = T(0);
             bool disc = true;
@@ -221,7 +221,7 @@ void oracle_make_rays_f32(const B200AtmoParams* p, const B200AtmoCamera* cam, co
             fragment_make_ray(inv_proj, inv_view, dp, depth[i], su, sv, &o, &d, &ld);
             float jitter = 0.f;
             if (tex && tex->blue_noise)
-                jitter = float(tex->blue_noise[size_t(y & (tex->bn_h - 1)) * tex->bn_w + (x & (tex->bn_w - 1))]) / 255.0f;
+                jitter = float(tex->blue_noise[size_t(y & 0xff) * tex->bn_w + (x & 0xff)]) / 255.0f;
             origin_depth[4 * i] = o.x; origin_depth[4 * i + 1] = o.y; origin_depth[4 * i + 2] = o.z; origin_depth[4 * i + 3] = ld;
             dir_jitter[4 * i] = d.x; dir_jitter[4 * i + 1] = d.y; dir_jitter[4 * i + 2] = d.z; dir_jitter[4 * i + 3] = jitter;
         }

@@ -10,7 +10,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "godot_atmosphere_shader_b200", "libb200atmo.so")
-KERNEL = "_ZN8b200atmo18render_rays_kernelILi0ELi0ENS_5RayIOEEEvNS_9DevConstsET1_"
+KERNEL = "_ZN8b200atmo18render_rays_kernelILi0ELi0ENS_5RayIOELb0EEEvNS_9DevConstsET1_"
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 ins, on = [], False

@@ -19,7 +19,7 @@ def test_library_loads_and_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/b200atmo.h but not exported"
     assert declared == set(context.EXPORTS)
-    assert lib.b200atmo_version() == 1
+    assert lib.b200atmo_version() == 2
 
 
 def test_struct_sizes_match():

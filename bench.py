@@ -2,22 +2,26 @@
 """bench.py — ray-steps/s of the atmosphere hot path on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]              our CUDA path
-  python bench.py --impl reference [--gpus N] [--steps K] ...      the CPU arm (scalar C++ oracle, all host threads)
+  python bench.py --impl reference [--gpus N] [--steps K] ...      the CPU arm (the reference's shaders compiled as C++)
 
-A "step" = one pass of the hot path over one frame of synthetic rays. Workload at N=1 = BASELINE.json
-configs[1]: 1920x1080, 32 in-scatter steps, LUT mode, no clouds, scene "demo",
-Camera B (every ray hits the atmosphere, so ray-steps = W*H*32). N>1: weak scaling, every rank renders
-its own 1080p tile of an N-tile offscreen target (no data-path collective; the optional NCCL all-gather
-of the RGBA tiles is measured separately under "gather").
+A "step" = one pass of the hot path over one frame of synthetic rays. Workload at N=1 = BASELINE.json configs[1]:
+1920x1080, 32 in-scatter steps, LUT mode, no clouds, scene "demo", camera B (every ray hits the
+atmosphere, so ray-steps = W*H*32). The line also carries configs[2] and configs[3] (clouds) as `configs.cfg3/cfg4`.
 
-`value`     : ray-steps/s, rays resident in HBM, kernel timed with CUDA events on the launch stream,
-              L2 flushed between timed iterations.
-`e2e`       : same metric through the host-buffer C-ABI (pinned host buffers), every step's depth H2D and RGBA D2H
-              inside the timed region: b200atmo_render_frame_host_submit / b200atmo_frame_wait over two pipeline
-              slots; the one-frame-at-a-time call b200atmo_render_frame_host is reported under e2e.synchronous.
-`roofline`  : algorithmic HBM bytes (48 B/ray: 2 x float4 in, 1 x float4 out) / kernel time vs the measured
-              copy bandwidth. NB this path is FP32-issue/MUFU bound at N=32; see DESIGN.md.
-`cpu_baseline`: the oracle (kind "port": the reference has no CPU implementation) on this box's host cores.
+`value`     : N=1: ray-steps/s of the render kernel, rays resident in HBM, CUDA events on the launch stream, L2 flushed
+              between timed iterations. N>1 (weak scaling, BASELINE configs[4] shape: every rank renders its own 1080p tile
+              of an N-tile offscreen target): ray-steps/s with the finished tiles DELIVERED to the consuming rank (rank 0)
+              as RGBA16F over NVLink by the render kernel itself (= `value_delivered`); `value_compute_only` is the kernel
+              without delivery, `delivery` lists every other mode (all-gather / root, float4 / half4 tiles, NCCL baseline),
+              `strong` is ONE frame sharded over the N GPUs.
+`e2e`       : same metric through the host-buffer C-ABI (pinned host buffers), every step's depth H2D and result D2H inside
+              the timed region: b200atmo_render_frame_host_submit_fmt / b200atmo_frame_wait over two pipeline slots, result
+              format RGBA16F (Godot's colour-target format; bit-exact RTN of the fp32 result); `e2e.fp32` is the float4 path.
+`roofline`  : algorithmic HBM bytes (48 B/ray: 2 x float4 in, 1 x float4 out) / kernel time vs the measured copy bandwidth.
+              NB this path is FP32-issue bound at N=32; `roofline_issue` is the roofline that binds.
+`parity_sample`: after the timed loop a strided sample of the very buffer the timed launches wrote is checked against the
+              oracle (gate = |err| / (1e-4*|want| + 2e-6), must be < 1; discard mask bit-exact). A failure exits non-zero.
+`cpu_baseline`: the reference's shader sources compiled as C++ (oracle/_ref) on this box's host cores.
 """
 import argparse
 import json
@@ -35,7 +39,7 @@ import numpy as np  # noqa: E402
 METRIC = "ray_steps_per_sec"
 UNIT = "ray-steps/s"
 ALGO_BYTES_PER_RAY = 48  # 32 B in (2 x float4) + 16 B out (RGBA f32)
-FRAME_BYTES_PER_PIXEL_IN, FRAME_BYTES_PER_PIXEL_OUT = 4, 16
+FRAME_BYTES_PER_PIXEL_IN = 4
 
 
 def parse_args():
@@ -49,34 +53,67 @@ def parse_args():
     ap.add_argument("--scatter-steps", type=int, default=32)
     ap.add_argument("--cloud-steps", type=int, default=0)
     ap.add_argument("--light", type=int, default=0)
-    ap.add_argument("--camera", choices=["A", "B"], default="B")
+    ap.add_argument("--camera", choices=["A", "B", "C"], default="B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-configs", action="store_true", help="skip the cfg3 / cfg4 sub-results (N=1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling runs (N>1)")
     ap.add_argument("--e2e-steps", type=int, default=60)
     return ap.parse_args()
 
 
+class Workload:
+    """One (size, variant, camera) point: BASELINE.json configs[k] as this bench runs it."""
+
+    def __init__(self, width, height, scatter_steps, cloud_steps=0, light=0, camera="B", name=None):
+        self.width, self.height, self.scatter_steps = width, height, scatter_steps
+        self.cloud_steps, self.light, self.camera, self.name = cloud_steps, light, camera, name
+
+    @property
+    def key(self):
+        return f"{self.width}x{self.height}x{self.scatter_steps}_c{self.cloud_steps}_l{self.light}_cam{self.camera}"
+
+    def describe(self):
+        return (f"{self.width}x{self.height} frame, {self.scatter_steps} in-scatter steps (LUT mode), "
+                + (f"{self.cloud_steps} cloud steps light={'cheap' if self.light == 1 else 'raymarched x6'}, " if self.light else "no clouds, ")
+                + f"scene demo (R=100,H=8,u_density=0.5), camera {self.camera}"
+                + {"B": " (all rays hit)", "C": " (cloud deck, all rays hit)", "A": " (orbit, 60 % hit)"}[self.camera])
+
+
 def workload_config(a, n_gpus):
+    wl = Workload(a.width, a.height, a.scatter_steps, a.cloud_steps, a.light, a.camera)
     return {
-        "workload": f"{a.width}x{a.height} frame, {a.scatter_steps} in-scatter steps (LUT mode), "
-                    + (f"{a.cloud_steps} cloud steps light={a.light}, " if a.light else "no clouds, ")
-                    + f"scene demo (R=100,H=8,u_density=0.5), camera {a.camera}"
-                    + (" (all rays hit)" if a.camera == "B" else ""),
+        "workload": wl.describe(),
         "width": a.width, "height": a.height, "scatter_steps": a.scatter_steps, "cloud_steps": a.cloud_steps,
         "light_mode": a.light, "camera": a.camera, "rays_per_gpu": a.width * a.height,
-        "parallelism": f"screen-tile shard x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "parallelism": (f"screen-tile shard x{n_gpus}: every rank renders its own tile, tiles delivered to rank 0 as RGBA16F "
+                        "by peer stores of the render kernel") if n_gpus > 1 else "single GPU",
         "l2": "flushed between timed iterations (256 MiB write)",
     }
 
 
-def build_scene(a):
+_TEXTURES = {}
+
+
+def textures(clouds):
+    from godot_atmosphere_shader_b200 import scenes
+    if "bn" not in _TEXTURES:
+        _TEXTURES["bn"] = scenes.blue_noise_tile()
+    if clouds and "shape" not in _TEXTURES:
+        _TEXTURES["shape"] = scenes.shape_texture(64, seed=1)
+        _TEXTURES["cube"] = scenes.coverage_cubemap(256, seed=1)
+    return _TEXTURES
+
+
+def build_scene(wl):
     from godot_atmosphere_shader_b200 import scenes
     p = scenes.demo_params()
-    cam = scenes.camera_b(a.width, a.height, p) if a.camera == "B" else scenes.camera_a(a.width, a.height)
-    depth = scenes.synth_depth(cam, p, a.width, a.height)
-    tex = dict(bn=scenes.blue_noise_tile())
-    if a.light:
-        tex["shape"] = scenes.shape_texture(64, seed=1)
-        tex["cube"] = scenes.coverage_cubemap(256, seed=1)
+    w, h = wl.width, wl.height
+    cam = {"A": lambda: scenes.camera_a(w, h), "B": lambda: scenes.camera_b(w, h, p), "C": lambda: scenes.camera_c(w, h, p)}[wl.camera]()
+    depth = scenes.synth_depth(cam, p, w, h)
+    t = textures(bool(wl.light))
+    tex = dict(bn=t["bn"])
+    if wl.light:
+        tex["shape"], tex["cube"] = t["shape"], t["cube"]
     return p, cam, depth, tex
 
 
@@ -132,8 +169,29 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def nvlink_counters(index):
+    """NVML NVLink data counters of one GPU, summed over its links, in bytes: {"tx": .., "rx": ..} or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        tx_id = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+        rx_id = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)
+        vals = nv.nvmlDeviceGetFieldValues(h, [(tx_id, 0xFFFFFFFF), (rx_id, 0xFFFFFFFF)])   # scope UINT_MAX = all links
+        out = {}
+        for name, v in zip(("tx", "rx"), vals):
+            if v.nvmlReturn != 0:
+                return None
+            vt = v.valueType
+            val = {0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(vt, v.value.ullVal)
+            out[name] = int(val) * 1024   # KiB
+        return out
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the scalar C++ oracle on all host threads
+# CPU arm: the reference's shader sources compiled as C++ on all host threads
 # ------------------------------------------------------------------------------------------------
 def usable_cpus():
     """Threads the CPU arm should use: min(hardware threads, scheduler affinity, cgroup CPU quota)."""
@@ -166,7 +224,12 @@ def usable_cpus():
     return n, info
 
 
-def cpu_frame_runner(a, budget_s_per_step):
+def oracle_textures(p, tex):
+    from oracle import pyoracle as O
+    return O.Textures(lut=O.bake_lut(p), shape=tex.get("shape"), cube_faces=tex.get("cube"), blue_noise=tex["bn"])
+
+
+def cpu_frame_runner(wl, budget_s_per_step):
     """Returns (run, info): run() renders one bounded sample on the host cores and returns (seconds, ray_steps).
 
     kind "reference": oracle/_ref — the reference's own GDShader sources compiled as C++ (oracle/ref/build_ref.py; built
@@ -174,18 +237,18 @@ def cpu_frame_runner(a, budget_s_per_step):
     kind "port" (only if that library is missing): the hand-written scalar C++ oracle on the same rows."""
     from oracle import pyoracle as O
     from oracle import pyref as R
-    p, cam, depth, tex = build_scene(a)
-    otex = O.Textures(lut=O.bake_lut(p), shape=tex.get("shape"), cube_faces=tex.get("cube"), blue_noise=tex["bn"])
-    var = O.variant(a.scatter_steps, a.cloud_steps, a.light)
+    p, cam, depth, tex = build_scene(wl)
+    otex = oracle_textures(p, tex)
+    var = O.variant(wl.scatter_steps, wl.cloud_steps, wl.light)
     threads, cpu_info = usable_cpus()
-    w, h = a.width, a.height
+    w, h = wl.width, wl.height
     use_ref = R.available()
     if use_ref:
         def render(stride):
             t0 = time.perf_counter()
             _, disc = R.render_frame(p, var, cam, otex, depth, w, h, threads=threads, row_stride=stride)
             dt = time.perf_counter() - t0
-            return dt, int((disc[::stride] == 0).sum()) * a.scatter_steps
+            return dt, int((disc[::stride] == 0).sum()) * wl.scatter_steps
     else:
         od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
 
@@ -196,7 +259,7 @@ def cpu_frame_runner(a, budget_s_per_step):
             t0 = time.perf_counter()
             _, disc = O.render_rays(p, var, fr, otex, s_od, s_dj, threads=threads)
             dt = time.perf_counter() - t0
-            return dt, int((disc == 0).sum()) * a.scatter_steps
+            return dt, int((disc == 0).sum()) * wl.scatter_steps
 
     # calibrate on 1/16 of the rows, then pick a row stride that keeps one step under the budget
     render(16)
@@ -210,16 +273,17 @@ def cpu_frame_runner(a, budget_s_per_step):
             else "scalar C++ oracle port -O2 no-FMA (oracle/_ref not built)")
     info = {"cores": threads, "host": cpu_info, "kind": "reference" if use_ref else "port",
             "sample": (f"full {w}x{h} frame" if stride == 1 else f"every {stride}th row of the {w}x{h} frame ({n_rows} rows)")
-                      + f", {a.scatter_steps} steps, {what}, {threads} std::thread workers"}
+                      + f", {wl.scatter_steps} steps, {what}, {threads} std::thread workers"}
     return (lambda: render(stride)), info
 
 
 def run_reference(a, rank, world):
     if rank != 0:
         return
+    wl = Workload(a.width, a.height, a.scatter_steps, a.cloud_steps, a.light, a.camera)
     total = a.steps + a.warmup
     budget = max(0.02, min(2.0, 150.0 / max(total, 1)))
-    run, info = cpu_frame_runner(a, budget)
+    run, info = cpu_frame_runner(wl, budget)
     for _ in range(a.warmup):
         run()
     t_sum, steps_sum = 0.0, 0
@@ -254,14 +318,12 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def load_ncu_facts(a):
+def load_ncu_facts(key):
     """Per-launch facts of the dominant kernel from the committed `ncu --set full` capture of this workload
     (profiles/roofline_traffic.json): DRAM bytes (read+write) and executed warp instructions. {} if none."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        d = json.load(open(path))
-        key = f"{a.width}x{a.height}x{a.scatter_steps}_c{a.cloud_steps}_l{a.light}_cam{a.camera}"
-        return d.get(key, {})
+        return json.load(open(path)).get(key, {})
     except Exception:
         return {}
 
@@ -292,11 +354,102 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def count_cloud_rays(p, od, dj, fr):
+    """Rays that enter raymarch_cloud (cloud_funcs.gdshaderinc:263-278), counted on the host in fp64 from the ray batch —
+    only the denominator of the cloud-steps/s metric, not part of any parity claim."""
+    o = od[:, :3].astype(np.float64)
+    d = dj[:, :3].astype(np.float64)
+    ld = od[:, 3].astype(np.float64)
+    C = np.array(fr.planet_center_view[:], dtype=np.float64)
+    R, H = float(p.planet_radius), float(p.atmosphere_height)
+
+    def ray_sphere(radius):
+        oc = o - C
+        b = (oc * d).sum(1)
+        qc = oc - b[:, None] * d
+        hh = radius * radius - (qc * qc).sum(1)
+        miss = hh < 0
+        s = np.sqrt(np.where(miss, 0.0, hh))
+        return np.where(miss, 1e6, -b - s), np.where(miss, 1e6, -b + s)
+
+    ax, ay = ray_sphere(R + H)
+    hit = ax != ay
+    gx, gy = ray_sphere(R)
+    gd = np.where(gx != gy, gx, 1e7)
+    f = float(p.sphere_depth_factor)
+    ld = ld * (1.0 - f) + gd * f
+    tx, ty = ray_sphere(R + float(p.cloud_top) * H)
+    bx, by = ray_sphere(R + float(p.cloud_bottom) * H)
+    t0 = np.maximum(tx, 0.0)
+    marched = hit & (tx != ty) & (t0 < ld) & ((ld > by) | (bx > 0.0))
+    return int(marched.sum())
+
+
+class Runner:
+    """One context + device buffers for one workload; the timed callables of bench.py."""
+
+    def __init__(self, torch, wl, local_rank):
+        from godot_atmosphere_shader_b200 import context
+        self.torch, self.wl = torch, wl
+        self.dev = torch.device("cuda", local_rank)
+        w, h = wl.width, wl.height
+        self.n_rays = w * h
+        self.p, self.cam, self.depth, self.tex = build_scene(wl)
+        self.ctx = context.AtmosphereContext(local_rank)
+        self.ctx.set_params(self.p)
+        self.ctx.set_variant(wl.scatter_steps, wl.cloud_steps, wl.light)
+        self.ctx.upload_blue_noise(self.tex["bn"])
+        if wl.light:
+            self.ctx.upload_shape3d(self.tex["shape"])
+            self.ctx.upload_coverage_cube(self.tex["cube"])
+        self.d_depth = torch.from_numpy(self.depth).to(self.dev)
+        self.d_od = torch.empty((self.n_rays, 4), dtype=torch.float32, device=self.dev)
+        self.d_dj = torch.empty((self.n_rays, 4), dtype=torch.float32, device=self.dev)
+        self.fr = self.ctx.make_rays(self.cam, self.d_depth, w, h, self.d_od, self.d_dj)
+        self.d_rgba = torch.empty((self.n_rays, 4), dtype=torch.float32, device=self.dev)
+        self.d_disc = torch.empty((self.n_rays,), dtype=torch.uint8, device=self.dev)
+        self.ctx.render_rays(self.fr, self.d_od, self.d_dj, self.n_rays, self.d_rgba, self.d_disc)
+        torch.cuda.synchronize()
+        self.hit_rays = int((self.d_disc == 0).sum().item())
+        self.ray_steps = self.hit_rays * wl.scatter_steps
+
+    def render_rays(self, grid=False):
+        self.ctx.render_rays(self.fr, self.d_od, self.d_dj, self.n_rays, self.d_rgba, None,
+                             grid=(self.wl.width, self.wl.height) if grid else None)
+
+    def parity_sample(self, min_rays=20000):
+        """A row-strided sample (>= min_rays rays) of self.d_rgba / self.d_disc — the buffers the timed launches wrote —
+        against the oracle (rays regenerated by the oracle's own front end). Outside every timed region."""
+        from oracle import pyoracle as O
+        wl, w, h = self.wl, self.wl.width, self.wl.height
+        otex = oracle_textures(self.p, self.tex)
+        od, dj, fr = O.make_rays(self.p, self.cam, otex, self.depth, w, h)
+        n_rows = max(1, -(-min_rays // w))
+        stride = max(1, h // n_rows)
+        rows = np.arange(stride // 2, h, stride)
+        sel = (rows[:, None] * w + np.arange(w)[None, :]).reshape(-1)
+        threads, _ = usable_cpus()
+        ref, rdisc = O.render_rays(self.p, O.variant(wl.scatter_steps, wl.cloud_steps, wl.light), fr, otex, od[sel], dj[sel], threads=threads)
+        idx = self.torch.from_numpy(sel).to(self.dev)
+        got = self.d_rgba.index_select(0, idx).cpu().numpy().astype(np.float64)
+        self.ctx.render_rays(self.fr, self.d_od, self.d_dj, self.n_rays, self.d_rgba, self.d_disc)   # same launch + the mask
+        self.torch.cuda.synchronize()
+        again = self.d_rgba.index_select(0, idx).cpu().numpy().astype(np.float64)
+        gdisc = self.d_disc.index_select(0, idx).cpu().numpy()
+        gate = np.abs(got - ref) / (1e-4 * np.abs(ref) + 2e-6)
+        return {"n": int(len(sel)), "rows": int(len(rows)), "max_gate": float(gate.max()), "discard_equal": bool(np.array_equal(gdisc, rdisc)),
+                "deterministic": bool(np.array_equal(got, again)), "against": "oracle (fp32 scalar restatement, pinned bit-for-bit to oracle/_ref)",
+                "tolerance": "|err| <= 1e-4*|want| + 2e-6 per channel (gate < 1)", "ok": bool(gate.max() < 1.0 and np.array_equal(gdisc, rdisc))}, (od, dj, fr)
+
+    def close(self):
+        self.ctx.close()
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from godot_atmosphere_shader_b200 import context
+    from godot_atmosphere_shader_b200 import abi
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback for the product path"
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
@@ -304,28 +457,11 @@ def run_ours(a, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     w, h, N = a.width, a.height, a.scatter_steps
     n_rays = w * h
-    p, cam, depth, tex = build_scene(a)
-
-    ctx = context.AtmosphereContext(local_rank)
-    ctx.set_params(p)
-    ctx.set_variant(N, a.cloud_steps, a.light)
-    ctx.upload_blue_noise(tex["bn"])
-    if a.light:
-        ctx.upload_shape3d(tex["shape"])
-        ctx.upload_coverage_cube(tex["cube"])
-    stream = torch.cuda.current_stream().cuda_stream
-
-    d_depth = torch.from_numpy(depth).to(dev)
-    d_od = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
-    d_dj = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
-    fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj, stream=stream)
-    d_rgba = torch.empty((n_rays, 4), dtype=torch.float32, device=dev)
-    d_disc = torch.empty((n_rays,), dtype=torch.uint8, device=dev)
-    ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, d_disc, stream=stream)
-    torch.cuda.synchronize()
-    hit_rays = int((d_disc == 0).sum().item())
-    ray_steps = hit_rays * N
-    checksum = float(d_rgba.double().sum().item())
+    main_wl = Workload(w, h, N, a.cloud_steps, a.light, a.camera)
+    R = Runner(torch, main_wl, local_rank)
+    ctx, cam, depth, fr, d_od, d_dj, d_depth, d_rgba = R.ctx, R.cam, R.depth, R.fr, R.d_od, R.d_dj, R.d_depth, R.d_rgba
+    hit_rays, ray_steps = R.hit_rays, R.ray_steps
+    failures = []
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -351,13 +487,24 @@ def run_ours(a, rank, world, local_rank):
         ms = sum(s.elapsed_time(e) for s, e in ev)
         return ms, wall
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_ms(fn, steps, warmup=3):
+        ms, _ = timed_loop(fn, steps, warmup)
+        return max_over_ranks(ms / steps)
+
+    # ---- the headline kernel: compute only -------------------------------------------------------------------------
     # A timed region that saw a hardware / thermal slowdown is rejected and measured again, once (all ranks decide together).
     remeasured = False
     for attempt in range(2):
         sampler = ClockSampler(local_rank)
         l0 = ctx.launch_count
         sampler.start()
-        ms_total, wall = timed_loop(lambda: ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None, stream=stream), a.steps, a.warmup)
+        ms_total, wall = timed_loop(lambda: ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None), a.steps, a.warmup)
         clocks = sampler.stop()
         launches = ctx.launch_count - l0 - a.warmup
         bad = bool(set(clocks.get("reasons", [])) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
@@ -369,180 +516,313 @@ def run_ours(a, rank, world, local_rank):
         remeasured = True
         time.sleep(2.0)
     clocks["remeasured_after_slowdown"] = remeasured
+    ms_compute = max_over_ranks(ms_total / a.steps)
+    value_compute = world * ray_steps / (ms_compute * 1e-3)
 
-    # max over ranks
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / a.steps
-    value = world * ray_steps / (ms_per_step * 1e-3)
+    # the timed buffer itself against the oracle (rank 0 checks; every rank rendered the same scene)
+    parity = None
+    if rank == 0:
+        parity, _ = R.parity_sample()
+        if not parity["ok"]:
+            failures.append(f"parity_sample of the timed buffer failed: {parity}")
 
+    few = max(20, a.steps // 4)
+    tiled_ms = timed_ms(lambda: R.render_rays(grid=True), few)
     # the frame API on device buffers (depth in, rays generated on the fly: 20 B/pixel instead of 48 B/ray)
     d_rgba2 = torch.empty_like(d_rgba)
-    fms, _ = timed_loop(lambda: ctx.render_frame(cam, d_depth, w, h, d_rgba2, None, stream=stream), max(20, a.steps // 4), 3)
-    tf = torch.tensor([fms / max(20, a.steps // 4)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-    frame_ms = float(tf.item())
+    frame_ms = timed_ms(lambda: ctx.render_frame(cam, d_depth, w, h, d_rgba2, None), few)
     frame_ok = bool(torch.equal(d_rgba2, d_rgba))
+    d_half = torch.empty((n_rays, 4), dtype=torch.float16, device=dev)
+    frame16_ms = timed_ms(lambda: ctx.render_frame(cam, d_depth, w, h, d_half, None, rgba_format=abi.COLOR_RGBA16F), few)
+    half_ok = bool(torch.equal(d_half, d_rgba.to(torch.float16)))
+    if not (frame_ok and half_ok):
+        failures.append(f"frame API differs from the ray API (fp32 identical: {frame_ok}, RGBA16F == RTN(fp32): {half_ok})")
 
-    # optional: compute + NCCL all-gather of the RGBA tiles (BASELINE config[4]); not part of `value`
-    gather = None
+    # ---- N>1: delivery of the tiles, strong scaling ------------------------------------------------------------------
+    delivery = strong = nvlink = None
+    ms_step, value, value_delivered = ms_compute, value_compute, None
     if world > 1:
-        gathered = torch.empty((world * n_rays, 4), dtype=torch.float32, device=dev)
+        delivery, nvlink, fails = measure_delivery(torch, dist, a, R, rank, world, timed_ms, few)
+        failures += fails
+        headline = delivery.get("root_rgba16f", {})
+        if "ms_per_step" in headline:
+            ms_step = headline["ms_per_step"]
+            value = value_delivered = world * ray_steps / (ms_step * 1e-3)
+        if not a.no_strong:
+            strong, fails = measure_strong(torch, dist, a, rank, world, local_rank, timed_ms)
+            failures += fails
 
-        def step_gather():
-            ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None, stream=stream)
-            dist.all_gather_into_tensor(gathered, d_rgba)
+    # ---- e2e through the host-buffer C-ABI (pinned host memory) --------------------------------------------------------
+    # Every step uploads that step's depth buffer and reads that step's result back. Pipelined submit/wait over two slots
+    # (frame k downloads while frame k+1 uploads and renders); result format RGBA16F (headline) and float4; plus the
+    # synchronous one-frame-at-a-time call.
+    h_depths = [torch.from_numpy(depth).pin_memory(), torch.from_numpy(depth.copy()).pin_memory()]
+    want32 = d_rgba.cpu().numpy()
+    want16 = d_rgba.to(torch.float16).cpu().numpy()
+    e2e = {}
+    for fmt_name, fmt, dtype, want in (("rgba16f", abi.COLOR_RGBA16F, torch.float16, want16), ("fp32", abi.COLOR_RGBA32F, torch.float32, want32)):
+        outs = [torch.zeros((n_rays, 4), dtype=dtype).pin_memory() for _ in range(2)]
 
-        gms, _ = timed_loop(step_gather, max(10, a.steps // 4), 3)
-        g = torch.tensor([gms / max(10, a.steps // 4)], dtype=torch.float64, device=dev)
-        dist.all_reduce(g, op=dist.ReduceOp.MAX)
-        gather = {"ms_per_step": float(g.item()), "value": world * ray_steps / (float(g.item()) * 1e-3), "unit": UNIT,
-                  "bytes_gathered_per_gpu": world * n_rays * 16, "collective": "ncclAllGather (torch.distributed)"}
-        # fused: the render kernel stores every finished RGBA value into all ranks' symmetric buffers over NVLink
-        # (NVLS multicast when the fabric offers it) -- the render IS the all-gather, no collective pass
-        from godot_atmosphere_shader_b200.sharding import SymmetricTiles, render_rays_and_gather_fused
-        fused = {}
-        for label, use_mc, use_tma in (("multicast", True, False), ("p2p", False, False), ("p2p_tma", False, True)):
-            try:
-                tiles = SymmetricTiles(world, n_rays, dev, use_multicast=use_mc, use_tma=use_tma)
-                if use_mc and not tiles.multicast_ptr:
-                    fused[label] = {"unavailable": "no NVLS multicast mapping on this fabric"}
-                    continue
-                fms2, _ = timed_loop(lambda: render_rays_and_gather_fused(ctx, fr, d_od, d_dj, n_rays, tiles, stream=stream),
-                                     max(10, a.steps // 4), 3)
-                fz = torch.tensor([fms2 / max(10, a.steps // 4)], dtype=torch.float64, device=dev)
-                dist.all_reduce(fz, op=dist.ReduceOp.MAX)
-                ok = bool(torch.equal(tiles.tensor.view(world * n_rays, 4), gathered))
-                fused[label] = {"ms_per_step": float(fz.item()), "value": world * ray_steps / (float(fz.item()) * 1e-3),
-                                "tiles_match_nccl": ok}
-                del tiles
-            except Exception as exc:  # symmetric memory unavailable (no P2P / driver support): report, do not fail the bench
-                fused[label] = {"unavailable": repr(exc)[:200]}
-        gather["fused"] = dict(fused, api="b200atmo_render_rays_peers + symmetric-memory barrier (timed incl. the barrier)")
-        # chunked + overlapped delivery through the frame API (sharding.render_tile_and_gather_overlapped)
-        from godot_atmosphere_shader_b200.sharding import render_tile_and_gather_overlapped
-        mine = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
-        best = None
-        for chunks in (2, 4, 8):
-            if h % chunks:
-                continue
-            slabs = torch.empty((chunks, world, h // chunks, w, 4), dtype=torch.float32, device=dev)
-            oms, _ = timed_loop(lambda: render_tile_and_gather_overlapped(ctx, cam, d_depth, w, h, mine, slabs, rank, world,
-                                                                          chunks, stream=stream), max(10, a.steps // 4), 3)
-            o = torch.tensor([oms / max(10, a.steps // 4)], dtype=torch.float64, device=dev)
-            dist.all_reduce(o, op=dist.ReduceOp.MAX)
-            ok = bool(torch.equal(slabs[:, rank].reshape(-1, 4), d_rgba)) and bool(torch.equal(slabs[:, (rank + 1) % world], slabs[:, rank]))
-            if best is None or float(o.item()) < best[1]:
-                best = (chunks, float(o.item()), ok)
-            del slabs
-        gather["overlapped"] = {"ms_per_step": best[1], "value": world * ray_steps / (best[1] * 1e-3), "chunks": best[0],
-                                "tiles_match": best[2], "layout": "chunk-major [chunks, world, rows, w, 4]"}
+        def pipelined(steps):
+            for k in range(steps):
+                ctx.frame_wait(k & 1)
+                ctx.render_frame_host_submit(cam, h_depths[k & 1], w, h, outs[k & 1], None, slot=k & 1, rgba_format=fmt)
+            ctx.frame_wait(0)
+            ctx.frame_wait(1)
 
-    # e2e through the host-buffer C-ABI (pinned host memory). Every step uploads that step's depth buffer and reads that
-    # step's RGBA back. Two forms: the synchronous call (one frame at a time), and the pipelined submit/wait pair over
-    # two slots (frame k downloads while frame k+1 uploads and renders) — the form a stream of frames uses.
-    h_depth = torch.from_numpy(depth).pin_memory()
-    h_rgba = torch.empty((n_rays, 4), dtype=torch.float32).pin_memory()
-    for _ in range(3):
-        ctx.render_frame_host(cam, h_depth, w, h, h_rgba, None)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.e2e_steps):
-        ctx.render_frame_host(cam, h_depth, w, h, h_rgba, None)
-    torch.cuda.synchronize()
-    e2e_sync_s = (time.perf_counter() - t0) / a.e2e_steps
-    e2e_ok = bool(np.array_equal(h_rgba.numpy(), d_rgba.cpu().numpy()))
-    h_depths = [h_depth, torch.from_numpy(depth.copy()).pin_memory()]
-    h_rgbas = [h_rgba, torch.empty((n_rays, 4), dtype=torch.float32).pin_memory()]
-    h_rgbas[0].zero_()
-
-    def pipelined(steps):
-        for k in range(steps):
-            ctx.frame_wait(k & 1)
-            ctx.render_frame_host_submit(cam, h_depths[k & 1], w, h, h_rgbas[k & 1], None, slot=k & 1)
-        ctx.frame_wait(0)
-        ctx.frame_wait(1)
-
-    pipelined(4)
-    barrier()
-    t0 = time.perf_counter()
-    pipelined(a.e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / a.e2e_steps
-    e2e_ok = e2e_ok and all(bool(np.array_equal(b.numpy(), d_rgba.cpu().numpy())) for b in h_rgbas[:min(2, a.e2e_steps)])
+        pipelined(4)
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(a.e2e_steps)
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / a.e2e_steps)
+        ok = all(bool(np.array_equal(b.numpy().view(np.uint8), want.view(np.uint8))) for b in outs)
+        for _ in range(3):
+            ctx.render_frame_host(cam, h_depths[0], w, h, outs[0], None, rgba_format=fmt)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            ctx.render_frame_host(cam, h_depths[0], w, h, outs[0], None, rgba_format=fmt)
+        torch.cuda.synchronize()
+        dts = max_over_ranks((time.perf_counter() - t0) / a.e2e_steps)
+        ok = ok and bool(np.array_equal(outs[0].numpy().view(np.uint8), want.view(np.uint8)))
+        if not ok:
+            failures.append(f"e2e {fmt_name}: host result differs from the device path")
+        e2e[fmt_name] = {"value": world * ray_steps / dt, "ms_per_step": dt * 1e3, "matches_device_path": ok,
+                         "h2d_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_IN, "d2h_bytes_per_step": n_rays * (8 if fmt else 16),
+                         "synchronous": {"value": world * ray_steps / dts, "ms_per_step": dts * 1e3,
+                                         "api": "b200atmo_render_frame_host_fmt (one frame at a time, 4 row bands over 2 streams)"}}
     # the whole transparent pass against Godot's RGBA16F colour target: depth + colour up, render + blend_mix, colour down
-    from godot_atmosphere_shader_b200 import abi as _abi
     h_color = torch.zeros((n_rays, 4), dtype=torch.float16).pin_memory()
     for _ in range(3):
-        ctx.composite_frame_host(cam, h_depth, w, h, h_color, color_format=_abi.COLOR_RGBA16F)
+        ctx.composite_frame_host(cam, h_depths[0], w, h, h_color, color_format=abi.COLOR_RGBA16F)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.e2e_steps):
-        ctx.composite_frame_host(cam, h_depth, w, h, h_color, color_format=_abi.COLOR_RGBA16F)
+        ctx.composite_frame_host(cam, h_depths[0], w, h, h_color, color_format=abi.COLOR_RGBA16F)
     torch.cuda.synchronize()
     comp_s = (time.perf_counter() - t0) / a.e2e_steps
-    te = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_sync_s = float(te[0].item()), float(te[1].item())
+
+    # ---- BASELINE configs[2], configs[3] as sub-results (N=1) -----------------------------------------------------------
+    sub = None
+    if world == 1 and not a.no_sub_configs and not a.light:
+        sub = {}
+        for name, swl in (("cfg3", Workload(1920, 1080, 8, 64, 1, "A", "cfg3")), ("cfg3_cloud_deck", Workload(1920, 1080, 8, 64, 1, "C", "cfg3")),
+                          ("cfg4", Workload(3840, 2160, 8, 128, 2, "A", "cfg4")), ("cfg4_cloud_deck", Workload(3840, 2160, 8, 128, 2, "C", "cfg4"))):
+            sub[name], fails = measure_sub_config(torch, swl, local_rank, timed_ms)
+            failures += fails
 
     if rank != 0:
-        return
+        R.close()
+        return 1 if failures else 0
     peak, peak_src = load_peaks()
-    facts = load_ncu_facts(a)
-    achieved = ALGO_BYTES_PER_RAY * n_rays / (ms_per_step * 1e-3) / 1e9
+    facts = load_ncu_facts(main_wl.key)
+    achieved = ALGO_BYTES_PER_RAY * n_rays / (ms_compute * 1e-3) / 1e9
     # second roofline: the resource that actually binds this kernel is the warp-instruction issue rate
     # (1 instr/clk/SMSP). Peak = 148 SMs x 4 SMSPs x SM clock under load.
     issue = None
     if facts.get("warp_instructions") and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         ipeak = sms * 4 * clocks["sm_mhz"] * 1e6
-        iach = facts["warp_instructions"] / (ms_per_step * 1e-3)
+        iach = facts["warp_instructions"] / (ms_compute * 1e-3)
         issue = {"bound": "issue", "achieved": iach / 1e9, "peak": ipeak / 1e9, "unit": "G warp-instr/s", "frac": iach / ipeak,
                  "warp_instructions_per_launch": facts["warp_instructions"], "source": facts.get("source")}
+    head = e2e["rgba16f"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "impl": "ours", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(a, world),
-        "mpixels_per_s": world * n_rays / (ms_per_step * 1e-3) / 1e6,
+        "value_compute_only": value_compute, "ms_per_step_compute_only": ms_compute,
+        "mpixels_per_s": world * n_rays / (ms_step * 1e-3) / 1e6,
         "hit_fraction": hit_rays / n_rays, "ray_steps_per_step": world * ray_steps,
-        "clocks": clocks,
-        "e2e": {"value": world * ray_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_IN,
-                "d2h_bytes_per_step": n_rays * FRAME_BYTES_PER_PIXEL_OUT, "ms_per_step": e2e_s * 1e3,
-                "api": "b200atmo_render_frame_host_submit + b200atmo_frame_wait (pinned host depth in, RGBA out; 2 pipeline "
-                       "slots: frame k's D2H overlaps frame k+1's H2D + kernel)",
-                "timer": "host perf_counter around the whole loop incl. the final waits, max over ranks", "matches_device_path": e2e_ok,
-                "host_numa_node_rank0": numa_node,
-                "synchronous": {"value": world * ray_steps / e2e_sync_s, "ms_per_step": e2e_sync_s * 1e3,
-                                "api": "b200atmo_render_frame_host (one frame at a time, 4 row bands over 2 streams)"}},
+        "clocks": clocks, "parity_sample": parity,
+        "e2e": {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms_per_step": head["ms_per_step"],
+                "api": "b200atmo_render_frame_host_submit_fmt(RGBA16F) + b200atmo_frame_wait (pinned host depth in, half4 RGBA out = "
+                       "bit-exact RTN-even of the fp32 result; 2 pipeline slots: frame k's D2H overlaps frame k+1's H2D + kernel)",
+                "timer": "host perf_counter around the whole loop incl. the final waits, max over ranks",
+                "matches_device_path": head["matches_device_path"], "host_numa_node_rank0": numa_node,
+                "synchronous": head["synchronous"], "fp32": e2e["fp32"]},
         "e2e_composite_rgba16f": {"ms_per_step": comp_s * 1e3, "value": ray_steps / comp_s, "unit": UNIT,
                                   "h2d_bytes_per_step": n_rays * 12, "d2h_bytes_per_step": n_rays * 8,
                                   "api": "b200atmo_composite_frame_host (rank 0; fp32 render + blend_mix into an RGBA16F frame)"},
         "gpu_launches": launches,
+        "ray_api_tile_mapped": {"ms_per_step": tiled_ms, "value": world * ray_steps / (tiled_ms * 1e-3), "unit": UNIT,
+                                "api": "b200atmo_render_rays_2d (warps cover 8x4 pixel tiles; bit-identical)"},
         "frame_api": {"ms_per_step": frame_ms, "value": world * ray_steps / (frame_ms * 1e-3), "unit": UNIT,
-                      "api": "b200atmo_render_frame (device depth in, 4 B + 16 B per pixel)", "bit_identical_to_ray_api": frame_ok},
+                      "api": "b200atmo_render_frame (device depth in, 4 B + 16 B per pixel)", "bit_identical_to_ray_api": frame_ok,
+                      "rgba16f": {"ms_per_step": frame16_ms, "equals_rtn_of_fp32": half_ok}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": facts.get("dram_bytes"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_RAY * n_rays,
-                     "kernel": "render_rays_kernel<V2, no clouds>" if not a.light else "render_rays_kernel<V2, clouds>",
-                     "note": "FP32-issue/MUFU bound at N=32 by construction (1.5 B/ray-step); see DESIGN.md"},
-        "timed_wall_s": wall, "checksum": checksum,
+                     "kernel": f"render_rays_kernel<V2, {'no clouds' if not a.light else 'clouds'}>",
+                     "note": (f"issue-bound by construction at N={N}: {ALGO_BYTES_PER_RAY / N:.2f} B of HBM traffic per ray-step against "
+                              "~46 issued instructions; see roofline_issue and DESIGN.md §5.1")},
+        "timed_wall_s": wall,
     }
     if issue:
         line["roofline_issue"] = issue
-    if gather:
-        line["gather"] = gather
+    if world > 1:
+        line["value_delivered"] = value_delivered
+        line["delivery"] = delivery
+        line["strong"] = strong
+        line["nvlink"] = nvlink
+    if sub:
+        line["configs"] = sub
     if world == 1 and not a.no_cpu_baseline:
-        run, info = cpu_frame_runner(a, budget_s_per_step=4.0)
+        run, info = cpu_frame_runner(main_wl, budget_s_per_step=4.0)
         run()
         ts = [run() for _ in range(3)]
         best = min(ts, key=lambda x: x[0])
         line["cpu_baseline"] = dict(info, value=best[1] / best[0], unit=UNIT, ms_per_step=best[0] * 1e3)
+    if failures:
+        line["failures"] = failures
     emit(line)
-    ctx.close()
+    R.close()
+    return 1 if failures else 0
+
+
+def measure_sub_config(torch, wl, local_rank, timed_ms):
+    """One cloud workload (BASELINE configs[2] / configs[3]): kernel time of the ray API (linear and tile-mapped) and of
+    the frame API, the cloud metrics of SURVEY.md §8(d), a parity sample of the timed buffer."""
+    R = Runner(torch, wl, local_rank)
+    fails = []
+    steps = 10 if wl.light == 2 else 30
+    lin_ms = timed_ms(lambda: R.render_rays(grid=False), steps)
+    til_ms = timed_ms(lambda: R.render_rays(grid=True), steps)
+    parity, (od, dj, fr) = R.parity_sample()     # checks R.d_rgba as the tile-mapped timed launches left it
+    if not parity["ok"]:
+        fails.append(f"{wl.name} camera {wl.camera}: parity_sample failed: {parity}")
+    d_out = torch.empty_like(R.d_rgba)
+    frm_ms = timed_ms(lambda: R.ctx.render_frame(R.cam, R.d_depth, wl.width, wl.height, d_out, None), steps)
+    if not torch.equal(d_out, R.d_rgba):
+        fails.append(f"{wl.name}: frame API differs from the ray API")
+    marched = count_cloud_rays(R.p, od, dj, fr)
+    best = min(lin_ms, til_ms)
+    evals_per_step = 7 if wl.light == 2 else 1
+    peak, _ = load_peaks()
+    ach = ALGO_BYTES_PER_RAY * R.n_rays / (best * 1e-3) / 1e9
+    out = {
+        "workload": wl.describe(), "ms_per_step": best, "ms_per_step_linear_mapping": lin_ms, "ms_per_step_tile_mapping": til_ms,
+        "ms_per_step_frame_api": frm_ms, "ray_steps_per_sec": R.ray_steps / (best * 1e-3), "mpixels_per_s": R.n_rays / (best * 1e-3) / 1e6,
+        "hit_fraction": R.hit_rays / R.n_rays, "rays_marched_through_clouds": marched,
+        "cloud_steps_per_sec": marched * wl.cloud_steps / (best * 1e-3),
+        "density_evals_per_sec": marched * wl.cloud_steps * evals_per_step / (best * 1e-3),
+        "density_evals_note": (f"rays_marched x {wl.cloud_steps} cloud steps x {evals_per_step} density evaluations per step as the reference "
+                               "shader executes them (SURVEY.md §2.1 work table); the kernel skips the ones that are exactly 0"),
+        "parity_sample": parity,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "note": "issue-bound: ~180 issued instructions per density evaluation on 12 texel reads that hit L1/L2 (DESIGN.md §5.2)"},
+    }
+    R.close()
+    return out, fails
+
+
+def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
+    """Weak scaling with the tiles delivered: every rank renders its tile and the render kernel itself stores the finished
+    pixels into the consuming ranks' symmetric buffers over NVLink. Modes: deliver-to-root / all-gather x float4 / half4,
+    NVLS multicast, and render + ncclAllGather as the baseline. Every mode is checked bit for bit against the NCCL result."""
+    from godot_atmosphere_shader_b200 import abi
+    from godot_atmosphere_shader_b200.sharding import SymmetricTiles, render_rays_and_gather_fused
+    ctx, fr, d_od, d_dj, n_rays, d_rgba, dev = R.ctx, R.fr, R.d_od, R.d_dj, R.n_rays, R.d_rgba, R.dev
+    fails, out = [], {}
+    gathered = torch.empty((world * n_rays, 4), dtype=torch.float32, device=dev)
+
+    def step_nccl():
+        ctx.render_rays(fr, d_od, d_dj, n_rays, d_rgba, None)
+        dist.all_gather_into_tensor(gathered, d_rgba)
+
+    ms = timed_ms(step_nccl, steps)
+    out["nccl_allgather_fp32"] = {"ms_per_step": ms, "value": world * R.ray_steps / (ms * 1e-3), "bytes_in_per_gpu": (world - 1) * n_rays * 16,
+                                  "api": "b200atmo_render_rays, then ncclAllGather (torch.distributed) — the baseline"}
+    gathered16 = gathered.to(torch.float16)
+    nvl = None
+    modes = [("root_rgba16f", dict(root=0, rgba_format=abi.COLOR_RGBA16F)),
+             ("root_fp32", dict(root=0, rgba_format=abi.COLOR_RGBA32F)),
+             ("allgather_rgba16f", dict(rgba_format=abi.COLOR_RGBA16F)),
+             ("allgather_fp32", dict(rgba_format=abi.COLOR_RGBA32F)),
+             ("allgather_fp32_multicast", dict(rgba_format=abi.COLOR_RGBA32F, use_multicast=True)),
+             ("allgather_rgba16f_tma", dict(rgba_format=abi.COLOR_RGBA16F, use_tma=True))]
+    for label, kw in modes:
+        try:
+            tiles = SymmetricTiles(world, n_rays, dev, **kw)
+            if kw.get("use_multicast") and not tiles.multicast_ptr:
+                out[label] = {"unavailable": "no NVLS multicast mapping on this fabric"}
+                continue
+            c0 = nvlink_counters(dev.index) if label == "root_rgba16f" else None
+            ms = timed_ms(lambda: render_rays_and_gather_fused(ctx, fr, d_od, d_dj, n_rays, tiles), steps)
+            c1 = nvlink_counters(dev.index) if label == "root_rgba16f" else None
+            want = gathered16 if kw["rgba_format"] == abi.COLOR_RGBA16F else gathered
+            ok = True
+            if kw.get("root") is None or rank == kw["root"]:
+                ok = bool(torch.equal(tiles.tensor.view(world * n_rays, 4), want))
+            okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            ok = bool(int(okt.item()))
+            if not ok:
+                fails.append(f"delivery mode {label}: tiles differ from render + ncclAllGather")
+            px = 8 if kw["rgba_format"] == abi.COLOR_RGBA16F else 16
+            out[label] = {"ms_per_step": ms, "value": world * R.ray_steps / (ms * 1e-3), "tiles_match_nccl": ok,
+                          "bytes_in_on_consumer_per_step": (world - 1) * n_rays * px,
+                          "consumer_ingress_GBps": (world - 1) * n_rays * px / (ms * 1e-3) / 1e9}
+            if c0 and c1:
+                # per timed_ms call: 3 warm-ups + `steps` timed launches
+                per = 3 + steps
+                nvl = {"mode": label, "gpu": dev.index, "launches_between_reads": per,
+                       "tx_bytes_per_step": (c1["tx"] - c0["tx"]) / per, "rx_bytes_per_step": (c1["rx"] - c0["rx"]) / per,
+                       "algorithmic_tx_bytes_per_step": tiles.bytes_sent_per_frame(n_rays),
+                       "algorithmic_rx_bytes_per_step": (world - 1) * n_rays * px if rank == 0 else 0,
+                       "source": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX (all links of this GPU), read around the timed loop"}
+            del tiles
+        except Exception as exc:  # symmetric memory unavailable (no P2P / driver support): report, do not fail the bench
+            out[label] = {"unavailable": repr(exc)[:200]}
+    out["api"] = "b200atmo_render_rays_peers + symmetric-memory barrier (timed incl. the barrier), double-buffered tiles"
+    # NVLink counters of every rank for the headline mode (rank 0 receives, the others send)
+    if nvl is not None:
+        objs = [None] * world
+        dist.all_gather_object(objs, nvl)
+        nvl = {"per_rank": objs}
+    return out, nvl, fails
+
+
+def measure_strong(torch, dist, a, rank, world, local_rank, timed_ms):
+    """Strong scaling: ONE frame sharded over the N GPUs (interleaved 8-row tiles), delivered to rank 0 as RGBA16F by the
+    render kernel's peer stores (and all-gathered as float4 for comparison); t1 = the same frame on one GPU, same run."""
+    from godot_atmosphere_shader_b200 import abi
+    from godot_atmosphere_shader_b200.sharding import SymmetricTiles, render_frame_sharded_fused
+    out, fails = {}, []
+    dev = torch.device("cuda", local_rank)
+    for name, wl, steps in (("1080p_n32", Workload(1920, 1080, 32, 0, 0, "B"), 30),
+                            ("4k_n32", Workload(3840, 2160, 32, 0, 0, "B"), 30),
+                            ("4k_rm128", Workload(3840, 2160, 8, 128, 2, "A"), 8)):
+        try:
+            R = Runner(torch, wl, local_rank)
+            w, h = wl.width, wl.height
+            one16 = torch.empty((h, w, 4), dtype=torch.float16, device=dev)
+            t1 = timed_ms(lambda: R.ctx.render_frame(R.cam, R.d_depth, w, h, one16, None, rgba_format=abi.COLOR_RGBA16F), steps)
+            res = {"workload": wl.describe(), "ms_one_gpu": t1, "pixels": w * h}
+            for label, kw, interleave in (("root_rgba16f_interleaved", dict(root=0, rgba_format=abi.COLOR_RGBA16F), True),
+                                          ("root_rgba16f_bands", dict(root=0, rgba_format=abi.COLOR_RGBA16F), False),
+                                          ("allgather_fp32_interleaved", dict(rgba_format=abi.COLOR_RGBA32F), True)):
+                tiles = SymmetricTiles(1, w * h, dev, **kw)
+                ms = timed_ms(lambda: render_frame_sharded_fused(R.ctx, R.cam, R.d_depth, w, h, tiles, interleave=interleave), steps)
+                ok = True
+                if kw.get("root") is None or rank == kw["root"]:
+                    want = one16 if kw["rgba_format"] == abi.COLOR_RGBA16F else R.d_rgba.view(h, w, 4)
+                    ok = bool(torch.equal(tiles.tensor.view(h, w, 4), want))
+                okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                ok = bool(int(okt.item()))
+                if not ok:
+                    fails.append(f"strong scaling {name}/{label}: sharded frame differs from the single-GPU frame")
+                res[label] = {"ms_per_frame": ms, "ray_steps_per_sec": R.ray_steps / (ms * 1e-3), "frame_matches_single_gpu": ok}
+                del tiles
+            out[name] = res
+            R.close()
+        except Exception as exc:
+            out[name] = {"unavailable": repr(exc)[:200]}
+    out["api"] = "b200atmo_render_frame_peers[_interleaved] + symmetric-memory barrier; ms_per_frame is the max over ranks incl. the barrier"
+    return out, fails
 
 
 _REAL_STDOUT = None
@@ -575,14 +855,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank, world)
-        return
+        return 0
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(a, rank, world, local_rank)
+        return run_ours(a, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
@@ -590,4 +870,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

@@ -24,7 +24,7 @@ EXPORTS = [
     "b200atmo_bake_optical_depth", "b200atmo_download_lut", "b200atmo_download_cube_padded", "b200atmo_render_rays",
     "b200atmo_render_rays_host", "b200atmo_render_frame", "b200atmo_render_frame_composite", "b200atmo_make_rays", "b200atmo_render_frame_host",
     "b200atmo_render_frame_host_submit", "b200atmo_frame_wait", "b200atmo_render_frame_composite_fmt", "b200atmo_composite_frame_host",
-    "b200atmo_render_frame_peers", "b200atmo_render_rays_peers",
+    "b200atmo_render_frame_peers", "b200atmo_render_rays_peers", "b200atmo_render_frame_peers_interleaved",
     "b200atmo_render_rays_2d", "b200atmo_render_frame_fmt", "b200atmo_render_frame_host_fmt", "b200atmo_render_frame_host_submit_fmt",
     "b200atmo_launch_count", "b200atmo_table_build_count",
 ]
@@ -74,6 +74,7 @@ def lib():
         L.b200atmo_render_frame_host_submit.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, vp, i32]
         L.b200atmo_frame_wait.argtypes = [vp, i32]
         L.b200atmo_render_frame_peers.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, C.POINTER(abi.B200AtmoPeerTargets), vp]
+        L.b200atmo_render_frame_peers_interleaved.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, C.POINTER(abi.B200AtmoPeerTargets), vp]
         L.b200atmo_render_rays_peers.argtypes = [vp, C.POINTER(B200AtmoFrame), vp, vp, C.c_size_t, C.POINTER(abi.B200AtmoPeerTargets), vp]
         L.b200atmo_render_frame_composite_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp]
         L.b200atmo_composite_frame_host.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32]
@@ -241,6 +242,11 @@ class AtmosphereContext:
         """Fused render + all-gather: rows [row_begin, row_end) go straight into every rank's symmetric buffer."""
         self._check(lib().b200atmo_render_frame_peers(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(row_begin),
                                                       int(h if row_end is None else row_end), C.byref(targets), stream))
+
+    def render_frame_peers_interleaved(self, cam: B200AtmoCamera, depth, w, h, targets, first_tile, tile_pitch, stream=None):
+        """Fused render + delivery of the 8-row tiles first_tile, first_tile + tile_pitch, ... (rank g of G: (g, G))."""
+        self._check(lib().b200atmo_render_frame_peers_interleaved(self._h, C.byref(cam), _dptr(depth), int(w), int(h), int(first_tile),
+                                                                  int(tile_pitch), C.byref(targets), stream))
 
     def render_rays_peers(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, targets, stream=None):
         self._check(lib().b200atmo_render_rays_peers(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),

@@ -783,8 +783,8 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     return B200ATMO_OK;
 }
 
-int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
-                                int row_end, const B200AtmoPeerTargets* targets, void* stream) {
+static int render_frame_peers_impl(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                                   int row_end, int row_pitch, const B200AtmoPeerTargets* targets, void* stream) {
     if (!ctx || !cam || !d_depth) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_peers: NULL argument");
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -793,7 +793,8 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
     if (rc != B200ATMO_OK) return rc;
     DevConsts c;
     if ((rc = frame_consts(ctx, cam, w, h, row_begin, row_end, c)) != B200ATMO_OK) return rc;
-    if (row_begin == row_end) return B200ATMO_OK;
+    if (row_begin >= row_end) return B200ATMO_OK;
+    c.row_pitch = row_pitch;
     if ((rc = bake_if_stale(ctx, s)) != B200ATMO_OK) return rc;
     io.depth = d_depth;
     io.n = size_t(w) * h;
@@ -801,6 +802,20 @@ int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, co
     CU_TRY(ctx, launch_render_frame_peers(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
     return B200ATMO_OK;
+}
+
+int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
+                                int row_end, const B200AtmoPeerTargets* targets, void* stream) {
+    return render_frame_peers_impl(ctx, cam, d_depth, w, h, row_begin, row_end, 8, targets, stream);
+}
+
+int b200atmo_render_frame_peers_interleaved(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                            int first_tile, int tile_pitch, const B200AtmoPeerTargets* targets, void* stream) {
+    if (first_tile < 0 || tile_pitch < 1 || first_tile >= tile_pitch)
+        return fail(ctx, B200ATMO_E_INVALID, "b200atmo_render_frame_peers_interleaved: need 0 <= first_tile < tile_pitch");
+    if (h < 1) return fail(ctx, B200ATMO_E_INVALID, "frame: bad size / row range");
+    const int row_begin = first_tile * 8 < h ? first_tile * 8 : h;   // more ranks than row tiles: nothing to do for this one
+    return render_frame_peers_impl(ctx, cam, d_depth, w, h, row_begin, h, 8 * tile_pitch, targets, stream);
 }
 
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,

@@ -148,6 +148,7 @@ inline void consts_set_camera(DevConsts& c, const B200AtmoParams& p, const B200A
     c.row_begin = row_begin;
     c.row_end = row_end;
     c.clip_box_half = cam.clip_box_size > 0.0f ? cam.clip_box_size * 0.5f : 0.0f;
+    c.row_pitch = 8;
 }
 
 }  // namespace b200atmo

@@ -62,6 +62,8 @@ struct DevConsts {
     int bn_w, bn_h;
     int fw, fh, row_begin, row_end;
     float clip_box_half;                   // MODE_FAR proxy cube half edge (0 = fullscreen)
+    int row_pitch;                         // frame kernel: rows between the 8-row tiles of consecutive blockIdx.y (8 = contiguous band;
+                                           // 8*world = the interleaved multi-GPU shard, b200atmo_render_frame_peers_interleaved)
 };
 
 struct RayIO {

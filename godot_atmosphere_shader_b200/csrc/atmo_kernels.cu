@@ -311,7 +311,7 @@ template <int MODEL, int LIGHT, class IO>
 __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = c.row_begin + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
     if (x >= c.fw || y >= c.row_end) return;
     const size_t i = size_t(y) * c.fw + x;
     f3 o, d;
@@ -398,7 +398,7 @@ template <class IO> static cudaError_t launch_rays_t(const DevConsts& c, const I
 template <class IO> static cudaError_t launch_frame_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     const int rows = c.row_end - c.row_begin;
     if (rows <= 0 || c.fw <= 0) return cudaSuccess;
-    const dim3 grid((c.fw + 15) / 16, (rows + 7) / 8);
+    const dim3 grid((c.fw + 15) / 16, (rows + c.row_pitch - 1) / c.row_pitch);   // row_pitch 8: one block row per 8 rows
     B200ATMO_DISPATCH(render_frame_kernel, grid, IO, c, io);
     return cudaGetLastError();
 }

@@ -116,6 +116,15 @@ def camera_b(w: int, h: int, params: B200AtmoParams = None) -> B200AtmoCamera:
     return make_camera(eye, (1.0, 0.0, 0.0), up=(0, 1, 0), aspect=w / h)
 
 
+def camera_c(w: int, h: int, params: B200AtmoParams = None, pitch_deg: float = 45.0) -> B200AtmoCamera:
+    """Camera C (cloud deck): 0.9*H above the surface on the sunlit +Z axis, above the cloud shell, looking 45 degrees down
+    into it — every ray hits the atmosphere and ~85 % of the pixels of the demo scene see cloud (camera B sees almost none)."""
+    p = params if params is not None else demo_params()
+    a = math.radians(pitch_deg)
+    eye = np.array([0.0, 0.0, p.planet_radius + 0.9 * p.atmosphere_height])
+    return make_camera(eye, (math.cos(a), 0.0, -math.sin(a)), up=(0, 0, 1), aspect=w / h)
+
+
 def synth_depth(cam: B200AtmoCamera, params: B200AtmoParams, w: int, h: int, planet_center=(0.0, 0.0, 0.0)) -> np.ndarray:
     """Depth buffer a Godot opaque pass would leave: the ground sphere where hit, else the clear value 0 (far)."""
     m = cam._meta

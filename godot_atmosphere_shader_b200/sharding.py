@@ -108,51 +108,143 @@ def peer_targets(buffer_ptrs, multicast_ptr=None, elem_offset: int = 0, first_pe
     return t
 
 
+def interleaved_rows(height: int, rank: int, world: int):
+    """Rows of rank `rank` under the interleaved shard: the 8-row tiles t with t % world == rank (numpy index array)."""
+    import numpy as np
+    tiles = np.arange(rank, (height + 7) // 8, world)
+    rows = (tiles[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    return rows[rows < height]
+
+
 class SymmetricTiles:
-    """One [slots, rays_per_slot, 4] fp32 buffer per rank in symmetric memory (torch.distributed._symmetric_memory: CUDA
-    VMM allocations exchanged between the ranks' processes, plus the NVLS multicast mapping when the fabric has one).
-    Rank r's render kernels store slot r of EVERY rank's buffer directly (`targets(rank)`), so after `barrier()` each GPU
-    holds all tiles: the render is the all-gather. PyTorch is the plumbing (allocation, rendezvous, barrier) only."""
+    """`depth` x [slots, rays_per_slot, 4] tile buffers per rank in symmetric memory (torch.distributed._symmetric_memory:
+    CUDA VMM allocations exchanged between the ranks' processes, plus the NVLS multicast mapping when the fabric has one).
+    Rank r's render kernels store slot r straight into the buffers of the ranks that consume it (`targets(rank)`), so
+    after `barrier()` those GPUs hold the tiles: the render is the delivery. PyTorch is the plumbing (allocation,
+    rendezvous, barrier) only.
+
+    rgba_format : abi.COLOR_RGBA32F (float4 tiles) or abi.COLOR_RGBA16F (half4 tiles — Godot's own colour-target format,
+                  half the NVLink bytes; each channel is the fp32 result rounded to nearest-even).
+    root        : None = all-gather (every rank receives every tile); r = deliver-to-root (only rank r's buffer is
+                  written: 1/world of the all-gather's fabric traffic).
+    depth       : number of buffers used round-robin, one per frame (`advance()`). With depth >= 2 and ONE barrier per
+                  frame no rank can overwrite a buffer a slower rank is still reading: a rank reaches frame k+2 only after
+                  every rank arrived at the barrier of frame k+1, which each rank queues AFTER its own reads of frame k.
+    All calls of one frame (render, barrier, the consumer's reads) must be queued on the same CUDA stream."""
 
     def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False, stagger: bool = True,
-                 use_tma: bool = False):
+                 use_tma: bool = False, rgba_format: int = 0, root=None, depth: int = 2):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
+        from .abi import COLOR_RGBA16F
+
         self.slots, self.rays_per_slot = int(slots), int(rays_per_slot)
         self.stagger = bool(stagger)
         self.use_tma = bool(use_tma)
+        self.rgba_format = int(rgba_format)
+        self.root = None if root is None else int(root)
+        self.depth = max(1, int(depth))
         group = group if group is not None else dist.group.WORLD
-        self.tensor = symm_mem.empty((self.slots, self.rays_per_slot, 4), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.tensor, group.group_name)
-        self.world = self.handle.world_size
-        self.rank = self.handle.rank
-        mc = getattr(self.handle, "multicast_ptr", 0) if use_multicast else 0
-        self.multicast_ptr = int(mc) if mc else None
-        self.buffer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        dtype = torch.float16 if self.rgba_format == COLOR_RGBA16F else torch.float32
+        self.tensors, self.handles = [], []
+        for _ in range(self.depth):
+            t = symm_mem.empty((self.slots, self.rays_per_slot, 4), dtype=dtype, device=device)
+            self.tensors.append(t)
+            self.handles.append(symm_mem.rendezvous(t, group.group_name))
+        self.world = self.handles[0].world_size
+        self.rank = self.handles[0].rank
+        self.cur = 0
+        self._mc = [int(getattr(hd, "multicast_ptr", 0) or 0) if (use_multicast and self.root is None) else 0 for hd in self.handles]
+        self._ptrs = [[int(q) for q in hd.buffer_ptrs] for hd in self.handles]
+
+    # the buffer of the current frame
+    @property
+    def tensor(self):
+        return self.tensors[self.cur]
+
+    @property
+    def handle(self):
+        return self.handles[self.cur]
+
+    @property
+    def multicast_ptr(self):
+        return self._mc[self.cur] or None
+
+    @property
+    def buffer_ptrs(self):
+        return self._ptrs[self.cur]
+
+    def advance(self):
+        """Switch to the next buffer (call once per frame, before rendering it)."""
+        self.cur = (self.cur + 1) % self.depth
 
     def targets(self, slot: int):
-        return peer_targets(self.buffer_ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot,
-                            first_peer=(self.rank + 1) % self.world if self.stagger else 0, use_tma=self.use_tma)
+        ptrs = self.buffer_ptrs if self.root is None else [self.buffer_ptrs[self.root]]
+        first = (self.rank + 1) % self.world if (self.stagger and self.root is None) else 0
+        return peer_targets(ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot, first_peer=first,
+                            use_tma=self.use_tma, rgba_format=self.rgba_format)
 
-    def barrier(self):
-        """Stream-ordered inter-rank barrier on the current CUDA stream: after it, every rank's stores have landed here."""
-        self.handle.barrier()
+    def bytes_sent_per_frame(self, pixels_rendered: int) -> int:
+        """NVLink egress of this rank for `pixels_rendered` pixels (stores into its own buffer do not touch the fabric)."""
+        from .abi import COLOR_RGBA16F
+        px = 8 if self.rgba_format == COLOR_RGBA16F else 16
+        if self.root is None:
+            return (self.world - 1) * pixels_rendered * px
+        return 0 if self.rank == self.root else pixels_rendered * px
+
+    def barrier(self, stream=None):
+        """Stream-ordered inter-rank barrier: after it, every rank's stores have landed here. `stream` = the
+        torch.cuda.Stream the render was queued on (None = the current stream); the barrier kernel is queued there."""
+        import torch
+        if stream is None:
+            self.handle.barrier()
+        else:
+            with torch.cuda.stream(stream):
+                self.handle.barrier()
 
 
-def render_rays_and_gather_fused(ctx, frame, d_origin_depth, d_dir_jitter, n_rays: int, tiles: "SymmetricTiles", stream=None):
-    """Weak-scaling delivery without a collective pass: this rank's rays are rendered straight into slot `rank` of every
-    rank's tile buffer; returns after the inter-rank barrier is queued (results are complete in stream order)."""
-    ctx.render_rays_peers(frame, d_origin_depth, d_dir_jitter, n_rays, tiles.targets(tiles.rank), stream=stream)
-    tiles.barrier()
+def _raw_stream(stream):
+    """torch.cuda.Stream | None -> the cudaStream_t the C-ABI takes (None = torch's current stream)."""
+    import torch
+    return (torch.cuda.current_stream() if stream is None else stream).cuda_stream
+
+
+def render_rays_and_gather_fused(ctx, frame, d_origin_depth, d_dir_jitter, n_rays: int, tiles: "SymmetricTiles", stream=None,
+                                 grid=None):
+    """Weak-scaling delivery without a collective pass: this rank's rays are rendered straight into slot `rank` of the
+    consuming ranks' tile buffers; returns after the inter-rank barrier is queued (results are complete in stream order).
+    `stream`: torch.cuda.Stream or None (current); `grid=(w, h)` selects the tile-mapped ray kernel."""
+    if grid is not None:
+        raise NotImplementedError("peer stores are implemented for the linear ray mapping and the frame API")
+    tiles.advance()
+    ctx.render_rays_peers(frame, d_origin_depth, d_dir_jitter, n_rays, tiles.targets(tiles.rank), stream=_raw_stream(stream))
+    tiles.barrier(stream)
     return tiles.tensor
 
 
-def render_frame_sharded_fused(ctx, cam, d_depth, width: int, height: int, tiles: "SymmetricTiles", stream=None):
-    """Screen-tile shard of ONE frame: rank g renders rows [g*H/G, (g+1)*H/G) into every rank's full-frame buffer
-    (`tiles` built with slots=1, rays_per_slot=width*height); returns the [height, width, 4] view after the barrier."""
-    b, e = band(height, tiles.rank, tiles.world)
-    ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(0), row_begin=b, row_end=e, stream=stream)
-    tiles.barrier()
+def render_frame_tile_fused(ctx, cam, d_depth, width: int, height: int, tiles: "SymmetricTiles", stream=None):
+    """Weak scaling through the FRAME API: this rank's whole width x height tile (its own camera / depth buffer) goes to
+    slot `rank` of the consuming ranks' buffers."""
+    tiles.advance()
+    ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(tiles.rank), stream=_raw_stream(stream))
+    tiles.barrier(stream)
+    return tiles.tensor
+
+
+def render_frame_sharded_fused(ctx, cam, d_depth, width: int, height: int, tiles: "SymmetricTiles", stream=None,
+                               interleave: bool = False):
+    """Screen-tile shard of ONE frame (strong scaling) into the consuming ranks' full-frame buffers (`tiles` built with
+    slots=1, rays_per_slot=width*height): rank g renders rows [g*H/G, (g+1)*H/G), or — `interleave` — the 8-row tiles
+    g, g+G, g+2G, ... (balanced when the work is not uniform over the frame). Returns the [height, width, 4] view after
+    the barrier is queued."""
+    tiles.advance()
+    if interleave:
+        ctx.render_frame_peers_interleaved(cam, d_depth, width, height, tiles.targets(0), tiles.rank, tiles.world,
+                                           stream=_raw_stream(stream))
+    else:
+        b, e = band(height, tiles.rank, tiles.world)
+        ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(0), row_begin=b, row_end=e, stream=_raw_stream(stream))
+    tiles.barrier(stream)
     return tiles.tensor.view(height, width, 4)

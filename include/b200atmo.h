@@ -289,6 +289,12 @@ typedef struct B200AtmoPeerTargets {
  * all-gather; the root's NVLink ingress is then the only loaded port). */
 int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
                                 int row_begin, int row_end, const B200AtmoPeerTargets* targets, void* stream);
+/* Interleaved screen-tile shard of ONE frame ("prefer interleaved tile-rows ... with a fixed, deterministic
+ * mapping"): the frame is cut into 8-row tiles and this call renders tiles first_tile, first_tile + tile_pitch, ... in one
+ * launch. Rank g of G passes (g, G). Unlike contiguous bands, every rank gets the same mix of sky, limb, ground and cloud
+ * rows, so the ranks finish together. Pixels are bit-identical to the unsharded frame. */
+int b200atmo_render_frame_peers_interleaved(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h,
+                                            int first_tile, int tile_pitch, const B200AtmoPeerTargets* targets, void* stream);
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth,
                                const float* d_dir_jitter, size_t n_rays, const B200AtmoPeerTargets* targets, void* stream);
 

@@ -127,6 +127,31 @@ def test_cameras_flags_and_parameter_corners_bit_exact():
             _assert_same(p, var, cam, tex, depth, w, h, what=what)
 
 
+def test_jitter_window_and_cloud_deck_camera_bit_exact():
+    """(1) `ivec2(px) & ivec2(0xff)` (planet_atmosphere_main.gdshaderinc:168-169) with a 512 x 512 jitter texture and a frame
+    wider than 256: the compiled shader reads only the top-left 256 x 256 texels, and so must the oracle. (2) camera C,
+    looking down into the cloud deck (most pixels see cloud), for the cheap and the raymarched cloud light."""
+    w, h = 300, 270
+    p = scenes.demo_params()
+    shape, cube, _ = Hh.demo_textures()
+    big = np.random.default_rng(3).integers(0, 256, size=(512, 512), dtype=np.uint8)
+    tex = O.Textures(lut=O.bake_lut(p), shape=shape, cube_faces=cube, blue_noise=big)
+    cam = scenes.camera_b(w, h, p)
+    depth = scenes.synth_depth(cam, p, w, h)
+    want, _ = _assert_same(p, O.variant(8, 0, abi.LIGHT_NONE), cam, tex, depth, w, h, what="512^2 jitter texture")
+    small = O.Textures(lut=tex.lut, shape=shape, cube_faces=cube, blue_noise=np.ascontiguousarray(big[:256, :256]))
+    again, _ = O.render_frame(p, O.variant(8, 0, abi.LIGHT_NONE), cam, small, depth, w, h)
+    assert np.array_equal(_bits(again), _bits(want))            # the other 3/4 of the texture are never read
+    w, h = 96, 54
+    cam = scenes.camera_c(w, h, p)
+    depth = scenes.synth_depth(cam, p, w, h)
+    tex = O.Textures(lut=O.bake_lut(p), shape=shape, cube_faces=cube, blue_noise=scenes.blue_noise_tile())
+    plain, _ = O.render_frame(p, O.variant(8, 0, abi.LIGHT_NONE), cam, tex, depth, w, h)
+    for var in (O.variant(8, 64, abi.LIGHT_CHEAP), O.variant(8, 64, abi.LIGHT_RAYMARCHED)):
+        want, wdisc = _assert_same(p, var, cam, tex, depth, w, h, what="camera C")
+        assert not wdisc.any() and (np.abs(want - plain).max(axis=-1) > 1e-6).mean() > 0.6
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_scenes_bit_exact(seed):
     """Random uniform blocks: planet scale over 3 decades, rotated + translated node, random cloud settings."""

@@ -22,6 +22,7 @@ LIGHT_RAYMARCHED = 2
 
 COLOR_RGBA32F = 0
 COLOR_RGBA16F = 1
+PIPELINE_SLOTS = 4   # B200ATMO_PIPELINE_SLOTS
 
 
 class B200AtmoParams(C.Structure):

@@ -780,6 +780,8 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     io.peer_offset = size_t(t->elem_offset);
     if (!valid_format(t->rgba_format)) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": unknown tile format");
     io.rgba_half = t->rgba_format == B200ATMO_COLOR_RGBA16F ? 1 : 0;
+    if (io.use_tma && io.rgba_half && (t->elem_offset & 1u))   // cp.async.bulk needs 16-byte aligned destinations
+        return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": TMA stores of half4 tiles need an even elem_offset");
     return B200ATMO_OK;
 }
 

@@ -174,6 +174,55 @@ B200_DEV float4 make_shape_cell(const float* __restrict__ shp, int nx, int ny, i
     return make_float4(p[0], p[1] - p[0], p[px], p[px + 1] - p[px]);
 }
 
+// Exact single-instruction forms of two-operation expressions in which one operation cannot round:
+//   0.5*(q + 1) == fma(q, 0.5, 0.5): scaling by a power of two commutes with rounding, so rn(q+1)/2 == rn((q+1)/2)
+//   2*h - 1     == fma(h, 2, -1),   c - 0.25*h == fma(h, -0.25, c): the product is exact, one rounding either way
+// (no subnormals in range). Bit-identical to the two-instruction forms, one issue slot less each.
+#ifndef B200ATMO_EXACT_FOLDS
+#define B200ATMO_EXACT_FOLDS 1
+#endif
+B200_DEV float half_of_sum1(float q) {
+#if B200ATMO_EXACT_FOLDS
+    return fmaf(q, 0.5f, 0.5f);
+#else
+    return 0.5f * (q + 1.0f);
+#endif
+}
+B200_DEV float twice_minus1(float h) {
+#if B200ATMO_EXACT_FOLDS
+    return fmaf(h, 2.0f, -1.0f);
+#else
+    return 2.0f * h - 1.0f;
+#endif
+}
+B200_DEV float minus_quarter(float c, float h) {
+#if B200ATMO_EXACT_FOLDS
+    return fmaf(h, -0.25f, c);
+#else
+    return c - 0.25f * h;
+#endif
+}
+// coord*n - 0.5 (texel coordinate of a normalised coordinate). When n is a power of two the product is exact and the fused
+// form is bit-identical; B200ATMO_POW2_TEX asserts that for the build (experiment knob, profiles/tune_clouds.py).
+B200_DEV float texel_coord(float s, float n) {
+#ifdef B200ATMO_POW2_TEX
+    return fmaf(s, n, -0.5f);
+#else
+    return s * n - 0.5f;
+#endif
+}
+// x - floor(x) for |x| < 2^22. B200ATMO_MAGIC_WRAP: floor by the magic-constant add instead of FRND.FLOOR (a conversion-
+// pipe instruction). At exact integers the magic form may return 1.0 where floorf gives 0.0: the same point of the
+// periodic interpolant (cell n instead of cell 0 of the repeat-padded volume, same texels, same weights).
+B200_DEV float wrap01(float x) {
+#ifdef B200ATMO_MAGIC_WRAP
+    const float f = ((x - 0.5f) + kMagic) - kMagic;
+    return x - f;
+#else
+    return x - floorf(x);
+#endif
+}
+
 // texture(u_cloud_coverage_cubemap, d).r — cloud_funcs:45 (seamless bilinear, LOD 0)
 B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, float y, float z) {
     const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
@@ -184,11 +233,12 @@ B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, f
     else                      { f = z >= 0.0f ? 4 : 5; ma = az; sc = z >= 0.0f ? x : -x; tc = -y; }
     const float inv_ma = rcp_approx(ma);
     // s = 0.5*(sc/ma + 1); xf = s*res - 0.5   (exact op order; the two divisions share one MUFU.RCP)
-    const float s = 0.5f * (div_refined(sc, ma, inv_ma) + 1.0f);
-    const float t = 0.5f * (div_refined(tc, ma, inv_ma) + 1.0f);
+    const float s = half_of_sum1(div_refined(sc, ma, inv_ma));
+    const float t = half_of_sum1(div_refined(tc, ma, inv_ma));
     float fx, fy;
-    const int xi = floor_frac(s * float(res) - 0.5f, fx) + 1;   // in [0, res] by construction (|sc|,|tc| <= ma)
-    const int yi = floor_frac(t * float(res) - 0.5f, fy) + 1;
+    const float resf = float(res);
+    const int xi = floor_frac(texel_coord(s, resf), fx) + 1;   // in [0, res] by construction (|sc|,|tc| <= ma)
+    const int yi = floor_frac(texel_coord(t, resf), fy) + 1;
     const unsigned rc = unsigned(res + 1);
     unsigned idx = (unsigned(f) * rc + unsigned(yi)) * rc + unsigned(xi);
     idx = min(idx, 6u * rc * rc - 1u);                            // NaN guard only
@@ -199,13 +249,13 @@ B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, f
 
 // texture(u_cloud_shape_texture, c).r — cloud_funcs:49 (repeat, trilinear, LOD 0)
 B200_DEV float sample_shape(const float4* __restrict__ cells, int nx, int ny, int nz, float cx, float cy, float cz) {
-    cx = cx - floorf(cx);  // repeat: wrap to [0,1]
-    cy = cy - floorf(cy);
-    cz = cz - floorf(cz);
+    cx = wrap01(cx);  // repeat: wrap to [0,1]
+    cy = wrap01(cy);
+    cz = wrap01(cz);
     float fx, fy, fz;
-    const int xi = floor_frac(cx * float(nx) - 0.5f, fx) + 1;   // in [0, n] by construction
-    const int yi = floor_frac(cy * float(ny) - 0.5f, fy) + 1;
-    const int zi = floor_frac(cz * float(nz) - 0.5f, fz) + 1;
+    const int xi = floor_frac(texel_coord(cx, float(nx)), fx) + 1;   // in [0, n] by construction
+    const int yi = floor_frac(texel_coord(cy, float(ny)), fy) + 1;
+    const int zi = floor_frac(texel_coord(cz, float(nz)), fz) + 1;
     const unsigned cxn = unsigned(nx + 1), cyn = unsigned(ny + 1);
     unsigned idx = (unsigned(zi) * cyn + unsigned(yi)) * cxn + unsigned(xi);
     idx = min(idx, cxn * cyn * unsigned(nz + 1) - 1u);            // NaN guard only
@@ -388,13 +438,13 @@ B200_DEV float cloud_height_ratio(const DevConsts& c, float len) {
 // get_density_full (:31-68) with |p| and height_ratio already computed; clamped density in [0,1].
 // Exact skip: outside the shell height_curve clamps to 0, so (..)*0*50-20 clamps to exactly 0.
 B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
-    const float a = 2.0f * hr - 1.0f;                                          // height_curve :25-29, exact
+    const float a = twice_minus1(hr);                                          // height_curve :25-29, exact
     const float hc = 1.0f - a * a;
     if (!(hc > 0.0f)) return 0.0f;
     const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;                         // u_cloud_coverage_rotation * p.xz :43, exact
     const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
     float coverage = sample_cube(c.cube_cells, c.cube_res, cpx, p.y, cpz);     // :45
-    coverage = coverage - 0.25f * hr + c.coverage_bias;                        // :46
+    coverage = minus_quarter(coverage, hr) + c.coverage_bias;                  // :46
     const float cov_term = mixf(-1.2f, 1.5f, coverage);
     // Exact early-out before the 3D fetch: the expression below is monotone in `shape` (every op is monotone under
     // round-to-nearest, hc > 0), so if it is <= 0 for the largest possible shape value it is <= 0 for the real one
@@ -477,20 +527,33 @@ B200_UNROLL(1)
     return f2{total_light, 1.0f - T_alpha};
 }
 
-// render_clouds (:249-324). Set-up and visibility test exact.
-template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px, f3 o, f3 d, float linear_depth, float jitter) {
+// render_clouds (:249-324) in three parts: set-up + visibility test (exact), the march, the blend.
+struct CloudRay {
+    bool active;      // the visibility test of :263-278 passed
+    f3 o, d;          // model-space ray (:286-287), not renormalised
+    float t0, t1;     // cloud_rs (:269-271)
+};
+B200_DEV CloudRay clouds_setup(const DevConsts& c, f3 o, f3 d, float linear_depth) {
+    CloudRay r;
+    r.active = false;
+    r.o = r.d = mk3(0.f, 0.f, 0.f);
+    r.t0 = r.t1 = 0.0f;
     const f3 C = ld3(c.C);
     const f2 rs_top = ray_sphere(C, c.cloud_top_h, o, d);
-    if (rs_top.x == rs_top.y) return;
+    if (rs_top.x == rs_top.y) return r;
     const f2 rs_bottom = ray_sphere(C, c.cloud_bottom_h, o, d);
-    const float t0 = fmaxf(rs_top.x, 0.0f);
-    const float t1 = fminf(rs_top.y, linear_depth);
-    if (!(t0 < linear_depth && (linear_depth > rs_bottom.y || rs_bottom.x > 0.0f))) return;  // :273-278
+    r.t0 = fmaxf(rs_top.x, 0.0f);
+    r.t1 = fminf(rs_top.y, linear_depth);
+    if (!(r.t0 < linear_depth && (linear_depth > rs_bottom.y || rs_bottom.x > 0.0f))) return r;  // :273-278
     float om[4], dm[4];
     mat4_mul(c.v2m, o.x, o.y, o.z, 1.0f, om);  // :286-287
     mat4_mul(c.v2m, d.x, d.y, d.z, 0.0f, dm);
-    const f2 rr = raymarch_cloud<LIGHT>(c, mk3(om[0], om[1], om[2]), mk3(dm[0], dm[1], dm[2]), t0, t1, jitter,
-                                        ld3(c.sun_dir_model));
+    r.o = mk3(om[0], om[1], om[2]);
+    r.d = mk3(dm[0], dm[1], dm[2]);
+    r.active = true;
+    return r;
+}
+B200_DEV void clouds_blend(const DevConsts& c, float4& px, f2 rr) {
     const float cl = rr.x, ca = rr.y;
     // blend_colors(self = atmosphere, over = cloud), util:61-69
     const float sa = 1.0f - ca;
@@ -508,6 +571,109 @@ template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px,
     px.z = mixf(bb, ab, c.cloud_blend);
     px.w = mixf(ba, aa, c.cloud_blend);
 }
+template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px, f3 o, f3 d, float linear_depth, float jitter) {
+    const CloudRay r = clouds_setup(c, o, d, linear_depth);
+    if (!r.active) return;
+    clouds_blend(c, px, raymarch_cloud<LIGHT>(c, r.o, r.d, r.t0, r.t1, jitter, ld3(c.sun_dir_model)));
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Warp-wide compaction of the raymarched cloud light (B200ATMO_LIGHT_QUEUE). The 6-step light march (:104-151) costs six
+// density evaluations but only runs for the samples whose density is > 0; in raymarch_cloud<RAYMARCHED> the lanes of a
+// warp without such a sample idle meanwhile. Here every lane marches its own ray, but a sample that needs the light
+// march is PUSHED into a per-warp shared-memory FIFO (position, height ratio, and the three factors the light value is
+// multiplied with); whenever 32 items are queued all 32 lanes pop one each and run the light march at full occupancy,
+// then every lane folds the results of ITS items into its accumulator in queue (= step) order. Per ray the arithmetic
+// and its order are exactly those of raymarch_cloud<RAYMARCHED>: results are bit-identical.
+//   q : 64 ring slots x 2 float4 per warp: {pos.xyz, height_ratio}, {shadow factor, density*step, T_clamped, light (out)}
+// Whether it pays depends on how coherent the lanes of a warp are (profiles/r02/warp_model.txt): measured in
+// profiles/r02/tune_clouds.txt.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long rotr64(unsigned long long v, unsigned s) { return s ? (v >> s) | (v << (64u - s)) : v; }
+__device__ __forceinline__ unsigned long long rotl64(unsigned long long v, unsigned s) { return s ? (v << s) | (v >> (64u - s)) : v; }
+
+__device__ __noinline__ f2 raymarch_cloud_light_queue(const DevConsts& c, const CloudRay r, float jitter, f3 sun, float4* q) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    if (!__any_sync(kFull, r.active)) return f2{0.0f, 0.0f};
+    const int steps = c.cloud_steps;
+    const f3 o = r.o, d = r.d;
+    const float t_begin = r.t0;
+    // march-length cap (:186-204), exact
+    const float max_d = mixf(c.march_ground, c.march_space, smoothstepf(c.march_hmin, c.march_hmax, sqrtf(dot3(o, o))));
+    const float t_end = t_begin + fminf(r.t1 - t_begin, max_d);
+    const float inv_steps = 1.0f / float(steps);
+    const float step_len = (t_end - t_begin) * inv_steps;
+    f3 pos = o + jitter * step_len * d + d * t_begin;  // :213, exact
+    const f3 dstep = d * step_len;
+    const float k = step_len * c.density_scale;
+    float T_clamped = 1.0f, T_alpha = 1.0f, total_light = 0.0f;
+    unsigned head = 0, count = 0;       // warp-uniform ring state
+    unsigned long long mine = 0;        // ring slots that hold items of this lane
+
+    auto drain = [&](unsigned n) {      // pop n <= 32 items, light-march them on n lanes, fold the results back in FIFO order
+        __syncwarp();
+        if (lane < n) {
+            const unsigned slot = (head + lane) & 63u;
+            const float4 a = q[2 * slot];
+            const float L = light_raymarched(c, mk3(a.x, a.y, a.z), sun, a.w);
+            reinterpret_cast<float*>(q + 2 * slot + 1)[3] = L;
+        }
+        __syncwarp();
+        const unsigned long long window = n >= 64u ? ~0ull : ((1ull << n) - 1ull);
+        unsigned long long m = rotr64(mine, head) & window;
+        while (m) {
+            const unsigned kbit = unsigned(__ffsll((long long)m)) - 1u;
+            m &= m - 1ull;
+            const float4 e = q[2 * ((head + kbit) & 63u) + 1];
+            const float light = e.w * e.x;                                    // get_light * mix(1, 0.002, shadow) :164
+            total_light = fmaf(light * e.y, e.z, total_light);                // :226
+        }
+        mine &= ~rotl64(window, head);
+        head = (head + n) & 63u;
+        count -= n;
+        __syncwarp();
+    };
+
+B200_UNROLL(1)
+    for (int i = 0; i < steps; ++i) {
+        bool hit = false;
+        float hr = 0.0f, sf = 0.0f, ds = 0.0f;
+        if (r.active) {
+            float inv;
+            const float len = sqrt_refined(dot3(pos, pos), inv);
+            hr = cloud_height_ratio(c, len);
+            const float dens01 = cloud_density(c, pos, hr);
+            if (dens01 > 0.0f) {
+                hit = true;
+                const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);
+                const float st = __saturatef((sdot + 0.3f) * (1.0f / 0.6f));
+                const float shadow = st * st * fmaf(-2.0f, st, 3.0f);
+                sf = fmaf(shadow, -0.998f, 1.0f);
+                ds = dens01 * k;
+                const float tr = ex2_approx(ds * -1.4426950408889634f);       // :221
+                T_clamped = fmaxf(T_clamped * tr, 0.005f);                    // :222-223
+                T_alpha *= tr;                                                // :228
+            }
+        }
+        const unsigned b = __ballot_sync(kFull, hit);
+        if (b) {
+            if (hit) {
+                const unsigned slot = (head + count + unsigned(__popc(b & ((1u << lane) - 1u)))) & 63u;
+                q[2 * slot] = make_float4(pos.x, pos.y, pos.z, hr);
+                q[2 * slot + 1] = make_float4(sf, ds, T_clamped, 0.0f);
+                mine |= 1ull << slot;
+            }
+            count += unsigned(__popc(b));
+            if (count >= 32u) drain(32u);
+        }
+        pos = pos + dstep;  // :236, exact
+    }
+    if (count) drain(count);
+    return f2{total_light, 1.0f - T_alpha};
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // NoiseCubemap content: "b200 gradient fBm v1" (see include/b200atmo.h). Exact arithmetic throughout (no fmaf), so the
@@ -605,6 +771,41 @@ template <int MODEL, int LIGHT> B200_DEV bool shade_ray(const DevConsts& c, f3 o
     if (LIGHT != B200ATMO_LIGHT_NONE) render_clouds<LIGHT>(c, out, o, d, linear_depth, jitter);
     return false;
 }
+
+#ifdef __CUDACC__
+// shade_ray for the raymarched-light variant with the per-warp light queue: ALL 32 lanes of the warp must call it
+// (`valid` = this lane has a ray); the scatter march and the cloud set-up run per lane, the cloud march cooperatively.
+template <int MODEL> __device__ __forceinline__ bool shade_ray_light_queue(const DevConsts& c, bool valid, f3 o, f3 d, float linear_depth,
+                                                                         float jitter, float4& out, float4* q) {
+    bool disc = true;
+    CloudRay cr;
+    cr.active = false;
+    cr.o = cr.d = mk3(0.f, 0.f, 0.f);
+    cr.t0 = cr.t1 = 0.0f;
+    out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        const f3 C = ld3(c.C);
+        const f2 rs_atmo = ray_sphere(C, c.atmo_radius, o, d);
+        if (rs_atmo.x != rs_atmo.y) {
+            disc = false;
+            const float t_begin = fmaxf(rs_atmo.x, 0.0f);
+            float t_end = fmaxf(rs_atmo.y, 0.0f);
+            const f2 rs_ground = ray_sphere(C, c.R, o, d);
+            float gd = 10000000.0f;
+            if (rs_ground.x != rs_ground.y) gd = rs_ground.x;
+            linear_depth = mixf(linear_depth, gd, c.sphere_depth_factor);  // :160
+            t_end = fminf(t_end, linear_depth);                            // :162
+            if (MODEL == B200ATMO_SCATTER_V1) out = scatter_v1(c, o, d, t_begin, t_end);
+            else out = scatter_v2(c, o, d, t_begin, t_end, jitter);
+            cr = clouds_setup(c, o, d, linear_depth);
+        }
+    }
+    __syncwarp();
+    const f2 rr = raymarch_cloud_light_queue(c, cr, jitter, ld3(c.sun_dir_model), q);
+    if (cr.active) clouds_blend(c, out, rr);
+    return disc;
+}
+#endif
 
 // MODE_FAR coverage (planet_atmosphere.gd:261-282,302-321): the node draws a BoxMesh of edge `atmo_clip_distance`
 // centred on itself, so the fragment shader only runs where that cube's front faces are rasterised and pass the

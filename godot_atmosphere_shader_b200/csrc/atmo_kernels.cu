@@ -201,6 +201,17 @@ cudaError_t launch_noise_cube(const B200AtmoNoise& noise, const float scale[3], 
 #define B200ATMO_BOUNDS __launch_bounds__(B200ATMO_BLOCK)
 #endif
 constexpr int kBlock = B200ATMO_BLOCK;
+// warp-wide compaction of the raymarched cloud light (atmo_device.cuh: raymarch_cloud_light_queue); 0 = per-thread march
+#ifndef B200ATMO_LIGHT_QUEUE
+#define B200ATMO_LIGHT_QUEUE 0
+#endif
+constexpr bool kLightQueue = B200ATMO_LIGHT_QUEUE != 0;
+// block size of the ray kernels that march clouds (ragged work: a block's warp slots are held until its slowest warp
+// is done, so smaller blocks keep more warps resident); tuning knob, profiles/r02/tune_clouds.txt
+#ifndef B200ATMO_CLOUD_BLOCK
+#define B200ATMO_CLOUD_BLOCK B200ATMO_BLOCK
+#endif
+__host__ __device__ constexpr int ray_block(int light) { return light ? B200ATMO_CLOUD_BLOCK : kBlock; }
 
 // Result store. Multi-GPU shards write straight into every rank's copy of a symmetric buffer over NVLink: with the NVLS
 // multicast mapping one 16-byte store is replicated by the NVSwitch to all GPUs (the render IS the all-gather, no
@@ -250,19 +261,43 @@ __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float
 // TILED (b200atmo_render_rays_2d): the batch is a c.fw x c.fh pixel grid; a warp covers an 8x4 pixel tile like the frame
 // kernel (four 128-byte segments per load instead of one 512-byte run), so its lanes enter and leave the cloud shell
 // together. A separate instantiation: the linear kernel keeps its code byte for byte.
+#ifdef B200ATMO_MIN_BLOCKS
+#define B200ATMO_RAY_BOUNDS(L) __launch_bounds__(ray_block(L), (L) ? 1 : B200ATMO_MIN_BLOCKS)
+#else
+#define B200ATMO_RAY_BOUNDS(L) __launch_bounds__(ray_block(L))
+#endif
 template <int MODEL, int LIGHT, class IO, bool TILED>
-__global__ void B200ATMO_BOUNDS render_rays_kernel(const __grid_constant__ DevConsts c, const IO io) {
+__global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_constant__ DevConsts c, const IO io) {
+    constexpr int BS = ray_block(LIGHT), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;   // block tile = (8*WX) x (4*WY) pixels
     size_t i;
+    bool valid;
     if (TILED) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-        const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-        if (x >= c.fw || y >= c.fh) return;
+        const int x = blockIdx.x * (8 * WX) + (warp % WX) * 8 + (lane & 7);
+        const int y = blockIdx.y * (4 * WY) + (warp / WX) * 4 + (lane >> 3);
+        valid = x < c.fw && y < c.fh;
         i = size_t(y) * c.fw + x;
     } else {
-        i = blockIdx.x * size_t(kBlock) + threadIdx.x;
-        if (i >= io.n) return;
+        i = blockIdx.x * size_t(BS) + threadIdx.x;
+        valid = i < io.n;
     }
+    if constexpr (LIGHT == B200ATMO_LIGHT_RAYMARCHED && kLightQueue) {
+        // every lane of the warp stays (lanes without a ray are passive): the cloud march is warp-cooperative
+        __shared__ float4 s_queue[BS / 32][128];
+        float4 od = make_float4(0.f, 0.f, 0.f, 0.f), dj = od, out;
+        if (valid) {
+            od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
+            dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
+        }
+        const bool disc = shade_ray_light_queue<MODEL>(c, valid, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out,
+                                                        s_queue[threadIdx.x >> 5]);
+        if (valid) {
+            store_rgba(io, i, out);
+            if (io.discard) io.discard[i] = disc ? 1 : 0;
+        }
+        return;
+    }
+    if (!valid) return;
     const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
     const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
     float4 out;
@@ -292,11 +327,14 @@ __global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_consta
     __syncthreads();
     if (threadIdx.x == 0) {
         const size_t left = io.n - base;
-        const unsigned bytes = unsigned(left < size_t(kBlock) ? left : size_t(kBlock)) * px_bytes;
+        const unsigned all = unsigned(left < size_t(kBlock) ? left : size_t(kBlock)) * px_bytes;
+        const unsigned bytes = all & ~15u;   // cp.async.bulk moves multiples of 16 bytes: an odd half4 tail pixel goes by a plain store
         const unsigned src = unsigned(__cvta_generic_to_shared(s_out));
         int r = io.first_peer;
         for (int k = 0; k < io.n_peers; ++k) {
             char* dst = static_cast<char*>(io.rgba_peers[r]) + (io.peer_offset + base) * px_bytes;
+            if (all != bytes) *reinterpret_cast<uint2*>(dst + bytes) = reinterpret_cast<const uint2*>(s_out)[bytes / 8u];
+            if (bytes == 0u) { r = (r + 1 == io.n_peers) ? 0 : r + 1; continue; }
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
             r = (r + 1 == io.n_peers) ? 0 : r + 1;
         }
@@ -384,14 +422,24 @@ cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, 
     } while (0)
 #define B200ATMO_COMMA ,
 
+template <int M, int L, class IO> static void launch_rays_one(const DevConsts& c, const IO& io, cudaStream_t s) {
+    constexpr int BS = ray_block(L), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;
+    if (c.fw > 0) {   // 2D batch: one (8*WX) x (4*WY) pixel tile per block
+        const dim3 grid((c.fw + 8 * WX - 1) / (8 * WX), (c.fh + 4 * WY - 1) / (4 * WY));
+        render_rays_kernel<M, L, IO, true><<<grid, BS, 0, s>>>(c, io);
+    } else {
+        render_rays_kernel<M, L, IO, false><<<unsigned((io.n + BS - 1) / BS), BS, 0, s>>>(c, io);
+    }
+}
 template <class IO> static cudaError_t launch_rays_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     if (io.n == 0) return cudaSuccess;
-    if (c.fw > 0) {   // 2D batch: 16x8 pixel tile per block
-        const dim3 grid((c.fw + 15) / 16, (c.fh + 7) / 8);
-        B200ATMO_DISPATCH(render_rays_kernel, grid, IO B200ATMO_COMMA true, c, io);
-    } else {
-        const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
-        B200ATMO_DISPATCH(render_rays_kernel, grid, IO B200ATMO_COMMA false, c, io);
+    switch ((scatter_model == B200ATMO_SCATTER_V1 ? 3 : 0) + light_mode) {
+        case 0: launch_rays_one<0, 0>(c, io, s); break;
+        case 1: launch_rays_one<0, 1>(c, io, s); break;
+        case 2: launch_rays_one<0, 2>(c, io, s); break;
+        case 3: launch_rays_one<1, 0>(c, io, s); break;
+        case 4: launch_rays_one<1, 1>(c, io, s); break;
+        default: launch_rays_one<1, 2>(c, io, s); break;
     }
     return cudaGetLastError();
 }

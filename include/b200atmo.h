@@ -278,7 +278,8 @@ typedef struct B200AtmoPeerTargets {
                                                that at any moment the ranks address DIFFERENT destinations (no incast on one NVLink port) */
     int32_t use_tma;                        /* b200atmo_render_rays_peers, P2P path: != 0 stages each block's 128 results in shared
                                                memory and sends them with one TMA bulk store (cp.async.bulk) per peer instead of one
-                                               STG.128 per thread and peer. Needs 16-byte aligned buffers and elem_offset. */
+                                               STG.128 per thread and peer. Needs 16-byte aligned buffers and elem_offset
+                                               (half4 tiles: an even elem_offset). */
     int32_t rgba_format;                    /* B200ATMO_COLOR_RGBA32F (float4 per pixel) or B200ATMO_COLOR_RGBA16F (half4 per pixel,
                                                each channel the fp32 result rounded to nearest-even): the tile format on the wire.
                                                Half the NVLink bytes; elem_offset counts pixels of that format. */
@@ -300,7 +301,8 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
 
 /*
  * Pipelined form of b200atmo_render_frame_host for a stream of frames (one per _process tick, or the tiles of an
- * offscreen target): enqueues H2D(depth) -> render -> D2H(rgba [, discard]) on pipeline slot `slot` and returns without
+ * offscreen target; B200ATMO_PIPELINE_SLOTS slots — with 3 in use the copy engine that downloads frame k never waits for the
+ * host to submit frame k+2): enqueues H2D(depth) -> render -> D2H(rgba [, discard]) on pipeline slot `slot` and returns without
  * waiting; b200atmo_frame_wait(ctx, slot) blocks until that frame's host buffers are complete. Each slot owns a stream
  * and device staging, so while frame k downloads (the PCIe-bound leg: 16 B/pixel), frame k+1 on the other slot uploads
  * and renders. Uniforms, variant and camera are captured at submit time. The host buffers must stay valid (and should be
@@ -308,7 +310,7 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
  * Texture uploads, re-bakes and b200atmo_destroy wait for frames in flight themselves.
  * Results are bit-identical to b200atmo_render_frame_host.
  */
-#define B200ATMO_PIPELINE_SLOTS 2
+#define B200ATMO_PIPELINE_SLOTS 4
 int b200atmo_render_frame_host_submit(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,
                                       int w, int h, float* h_rgba, uint8_t* h_discard, int slot);
 int b200atmo_render_frame_host_submit_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* h_depth,

@@ -274,7 +274,7 @@ def test_pipelined_host_frames_equal_the_synchronous_call(cuda_ctx_factory):
         ctx.render_frame_host_submit(frames[0][0], frames[0][1], w, h, frames[0][2], None, slot=1)
     assert ei.value.code == abi.E_STATE
     with pytest.raises(B200AtmoError):
-        ctx.frame_wait(2)
+        ctx.frame_wait(abi.PIPELINE_SLOTS)
     ctx.frame_wait(0)
     ctx.frame_wait(1)
     ctx.frame_wait(1)                             # idempotent

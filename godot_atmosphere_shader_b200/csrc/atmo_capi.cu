@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "atmo_consts.h"
 #include "atmo_internal.h"
@@ -25,6 +26,7 @@ struct b200atmo_ctx {
     uint8_t* d_cube_pad_u8 = nullptr;
     float4* d_cube_cells = nullptr;
     int cube_res = 0;
+    float cube_max = 1.0f;         // largest coverage texel / 255 (bounds the cloud density, atmo_consts.h cloud_hc_min)
     float4* d_shape_cells = nullptr;
     int nx = 0, ny = 0, nz = 0;
     uint8_t* d_blue = nullptr;
@@ -116,6 +118,7 @@ DeviceTextures textures_of(const b200atmo_ctx* ctx) {
     t.lut_cells = ctx->d_lut_cells;
     t.cube_cells = ctx->d_cube_cells;
     t.cube_res = ctx->cube_res;
+    t.cube_max = ctx->cube_max;
     t.shape_cells = ctx->d_shape_cells;
     t.nx = ctx->nx;
     t.ny = ctx->ny;
@@ -179,6 +182,20 @@ int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_
     CU_TRY(ctx, d_pad.alloc(pad * sizeof(float)));
     CU_TRY(ctx, d_cells.alloc(size_t(6) * (res + 1) * (res + 1) * sizeof(float4)));
     CU_TRY(ctx, cudaMemcpyAsync(d_raw.p, d_src ? d_src : h_faces6, raw, d_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    // largest texel (the seamless apron only repeats face texels or averages three of them): faces generated on the device
+    // are read back once for it (uploads are rare)
+    unsigned max_texel = 0;
+    {
+        std::vector<uint8_t> tmp;
+        const uint8_t* src = h_faces6;
+        if (d_src) {
+            tmp.resize(raw);
+            CU_TRY(ctx, cudaMemcpyAsync(tmp.data(), d_src, raw, cudaMemcpyDeviceToHost, s));
+            CU_TRY(ctx, cudaStreamSynchronize(s));
+            src = tmp.data();
+        }
+        for (size_t i = 0; i < raw; ++i) max_texel = src[i] > max_texel ? src[i] : max_texel;
+    }
     CU_TRY(ctx, launch_cube_pad(d_raw.as<uint8_t>(), res, d_pad8.as<uint8_t>(), d_pad.as<float>(), d_cells.as<float4>(), s));
     ctx->launches += 2;
     CU_TRY(ctx, cudaStreamSynchronize(s));
@@ -187,6 +204,7 @@ int upload_cube(b200atmo_ctx* ctx, const uint8_t* h_faces6, int res, cudaStream_
     ctx->d_cube_pad_u8 = d_pad8.release<uint8_t>();
     ctx->d_cube_cells = d_cells.release<float4>();
     ctx->cube_res = res;
+    ctx->cube_max = float(max_texel) / 255.0f;
     return B200ATMO_OK;
 }
 

@@ -24,6 +24,7 @@ struct DeviceTextures {
     int cube_res = 0;
     const float4* shape_cells = nullptr;
     int nx = 0, ny = 0, nz = 0;
+    float cube_max = 1.0f;   // largest texel of the coverage cube as the sampler returns it (u8/255); 1 = unknown
     const uint8_t* blue_noise = nullptr;
     int bn_w = 0, bn_h = 0;
 };
@@ -41,6 +42,37 @@ inline void mat4_mul_mat(const float* a, const float* b, float* out) {
 }
 inline float pow4(float x) { return x * x * x * x; }
 }  // namespace hostmath
+
+// Largest height-curve value hc for which the cloud density (cloud_funcs:39-64) is exactly 0 whatever the coverage and
+// shape texels are. The shader's expression is monotone non-decreasing in the coverage sample, in the shape term and
+// (for a positive sum) in hc under round-to-nearest, so evaluating it IN THE SHADER'S OWN fp32 OP ORDER with the upper
+// bounds of both gives an upper bound of the real value; where that bound is <= 0 the clamped density is 0. Bilinear
+// filtering (fma lerps of texels <= cube_max) can exceed cube_max by a few ulps at most: 8 ulps of slack are added.
+// In the shell 0 < height_ratio < 1, so `coverage - 0.25*hr` never exceeds the coverage sample. Found by bisection over
+// the float bits of hc in (0, 1]; 0 when no useful bound exists.
+inline float cloud_hc_min(float cube_max, float coverage_bias, float shape_hi_m01) {
+    const float tex_hi = cube_max * (1.0f + 8.0f * 1.1920929e-7f);
+    const float cov_hi = tex_hi + coverage_bias;
+    const float covterm_hi = -1.2f * (1.0f - cov_hi) + 1.5f * cov_hi;             // GLSL mix(-1.2, 1.5, cov) as the kernels evaluate it
+    const float total_hi = shape_hi_m01 + covterm_hi;
+    if (!(total_hi > 0.0f)) return 1.0f;                                         // hc <= 1 always: no sample can be dense
+    auto positive = [&](float hc) { return total_hi * hc * 50.0f - 20.0f > 0.0f; };
+    if (positive(1.1754944e-38f)) return 0.0f;
+    if (!positive(1.0f)) return 1.0f;
+    uint32_t lo, hi;                                                             // invariant: !positive(lo), positive(hi)
+    float flo = 1.1754944e-38f, fhi = 1.0f;
+    std::memcpy(&lo, &flo, 4);
+    std::memcpy(&hi, &fhi, 4);
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        float fm;
+        std::memcpy(&fm, &mid, 4);
+        if (positive(fm)) hi = mid;
+        else lo = mid;
+    }
+    std::memcpy(&flo, &lo, 4);
+    return flo;
+}
 
 // Uniform-only part (everything that does not depend on the frame).
 inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Variant& v, const DeviceTextures& t) {
@@ -94,6 +126,7 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
         const float shape_hi = c.shape_invert ? 1.0f - lo : hi;
         c.shape_hi_m01 = shape_hi - 0.2f * 0.5f;
     }
+    c.hc_min = cloud_hc_min(t.cube_max, c.coverage_bias, c.shape_hi_m01);
     c.cube_cells = t.cube_cells;
     c.cube_res = t.cube_res;
     c.shape_cells = t.shape_cells;

@@ -27,6 +27,12 @@
 #ifndef B200ATMO_SCATTER_UNROLL
 #define B200ATMO_SCATTER_UNROLL 8
 #endif
+#ifndef B200ATMO_LIGHT_UNROLL
+#define B200ATMO_LIGHT_UNROLL 1
+#endif
+#ifndef B200ATMO_CLOUD_UNROLL
+#define B200ATMO_CLOUD_UNROLL 1
+#endif
 #define B200_PRAGMA(x) _Pragma(#x)
 #ifdef __CUDACC__
 #define B200_DEV __device__ __forceinline__
@@ -202,14 +208,14 @@ B200_DEV float minus_quarter(float c, float h) {
     return c - 0.25f * h;
 #endif
 }
-// coord*n - 0.5 (texel coordinate of a normalised coordinate). When n is a power of two the product is exact and the fused
-// form is bit-identical; B200ATMO_POW2_TEX asserts that for the build (experiment knob, profiles/tune_clouds.py).
-B200_DEV float texel_coord(float s, float n) {
-#ifdef B200ATMO_POW2_TEX
-    return fmaf(s, n, -0.5f);
-#else
+// coord*n - 0.5 (texel coordinate of a normalised coordinate). When n is a power of two the product is exact, so the fused
+// form rounds once to the same value: bit-identical, one issue slot less. POW2 = every dimension of the coverage cube and
+// of the shape volume is a power of two (the usual case: Godot's NoiseTexture3D is 64^3, the NoiseCubemap 256^2); the
+// host selects the kernel instantiation (bit 2 of the LIGHT template argument, kLightPow2).
+constexpr int kLightPow2 = 4;
+template <bool POW2> B200_DEV float texel_coord(float s, float n) {
+    if (POW2) return fmaf(s, n, -0.5f);
     return s * n - 0.5f;
-#endif
 }
 // x - floor(x) for |x| < 2^22. B200ATMO_MAGIC_WRAP: floor by the magic-constant add instead of FRND.FLOOR (a conversion-
 // pipe instruction). At exact integers the magic form may return 1.0 where floorf gives 0.0: the same point of the
@@ -224,7 +230,7 @@ B200_DEV float wrap01(float x) {
 }
 
 // texture(u_cloud_coverage_cubemap, d).r — cloud_funcs:45 (seamless bilinear, LOD 0)
-B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, float y, float z) {
+template <bool POW2> B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, float y, float z) {
     const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
     int f;
     float sc, tc, ma;
@@ -237,8 +243,8 @@ B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, f
     const float t = half_of_sum1(div_refined(tc, ma, inv_ma));
     float fx, fy;
     const float resf = float(res);
-    const int xi = floor_frac(texel_coord(s, resf), fx) + 1;   // in [0, res] by construction (|sc|,|tc| <= ma)
-    const int yi = floor_frac(texel_coord(t, resf), fy) + 1;
+    const int xi = floor_frac(texel_coord<POW2>(s, resf), fx) + 1;   // in [0, res] by construction (|sc|,|tc| <= ma)
+    const int yi = floor_frac(texel_coord<POW2>(t, resf), fy) + 1;
     const unsigned rc = unsigned(res + 1);
     unsigned idx = (unsigned(f) * rc + unsigned(yi)) * rc + unsigned(xi);
     idx = min(idx, 6u * rc * rc - 1u);                            // NaN guard only
@@ -248,14 +254,14 @@ B200_DEV float sample_cube(const float4* __restrict__ cells, int res, float x, f
 }
 
 // texture(u_cloud_shape_texture, c).r — cloud_funcs:49 (repeat, trilinear, LOD 0)
-B200_DEV float sample_shape(const float4* __restrict__ cells, int nx, int ny, int nz, float cx, float cy, float cz) {
+template <bool POW2> B200_DEV float sample_shape(const float4* __restrict__ cells, int nx, int ny, int nz, float cx, float cy, float cz) {
     cx = wrap01(cx);  // repeat: wrap to [0,1]
     cy = wrap01(cy);
     cz = wrap01(cz);
     float fx, fy, fz;
-    const int xi = floor_frac(texel_coord(cx, float(nx)), fx) + 1;   // in [0, n] by construction
-    const int yi = floor_frac(texel_coord(cy, float(ny)), fy) + 1;
-    const int zi = floor_frac(texel_coord(cz, float(nz)), fz) + 1;
+    const int xi = floor_frac(texel_coord<POW2>(cx, float(nx)), fx) + 1;   // in [0, n] by construction
+    const int yi = floor_frac(texel_coord<POW2>(cy, float(ny)), fy) + 1;
+    const int zi = floor_frac(texel_coord<POW2>(cz, float(nz)), fz) + 1;
     const unsigned cxn = unsigned(nx + 1), cyn = unsigned(ny + 1);
     unsigned idx = (unsigned(zi) * cyn + unsigned(yi)) * cxn + unsigned(xi);
     idx = min(idx, cxn * cyn * unsigned(nz + 1) - 1u);            // NaN guard only
@@ -437,20 +443,26 @@ B200_DEV float cloud_height_ratio(const DevConsts& c, float len) {
 
 // get_density_full (:31-68) with |p| and height_ratio already computed; clamped density in [0,1].
 // Exact skip: outside the shell height_curve clamps to 0, so (..)*0*50-20 clamps to exactly 0.
-B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
+template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
     const float a = twice_minus1(hr);                                          // height_curve :25-29, exact
     const float hc = 1.0f - a * a;
+    // outside the shell (hc <= 0) and in the rim of the shell where not even the largest coverage texel with the largest
+    // shape value reaches a positive density (hc <= c.hc_min, an exact bound: atmo_consts.h cloud_hc_min)
+#ifdef B200ATMO_NO_HCMIN   // tuning knob: the plain shell test
     if (!(hc > 0.0f)) return 0.0f;
+#else
+    if (!(hc > c.hc_min)) return 0.0f;
+#endif
     const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;                         // u_cloud_coverage_rotation * p.xz :43, exact
     const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
-    float coverage = sample_cube(c.cube_cells, c.cube_res, cpx, p.y, cpz);     // :45
+    float coverage = sample_cube<POW2>(c.cube_cells, c.cube_res, cpx, p.y, cpz);     // :45
     coverage = minus_quarter(coverage, hr) + c.coverage_bias;                  // :46
     const float cov_term = mixf(-1.2f, 1.5f, coverage);
     // Exact early-out before the 3D fetch: the expression below is monotone in `shape` (every op is monotone under
     // round-to-nearest, hc > 0), so if it is <= 0 for the largest possible shape value it is <= 0 for the real one
     // and the clamped density is exactly 0. ~3/4 of the in-shell samples of the demo scene end here.
     if (!((c.shape_hi_m01 + cov_term) * hc * 50.0f - 20.0f > 0.0f)) return 0.0f;
-    const float tex = sample_shape(c.shape_cells, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
+    const float tex = sample_shape<POW2>(c.shape_cells, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
                                    p.y * c.shape_scale, p.z * c.shape_scale);
     float shape = mixf(0.5f, tex, c.shape_factor);                             // :48-50
     if (c.shape_invert) shape = 1.0f - shape;                                  // :57-59
@@ -461,16 +473,16 @@ B200_DEV float cloud_density(const DevConsts& c, f3 p, float hr) {
 }
 
 // get_light_raymarched (:104-151)
-B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0) {
+template <bool POW2> B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0) {
     float step_len = c.light_reach * (1.0f / 6.0f);   // reach * inv_steps
     float transm = 1.0f;                               // 1 - alpha
-B200_UNROLL(1)
+B200_UNROLL(B200ATMO_LIGHT_UNROLL)
     for (int i = 0; i < 6; ++i) {
         const float t = float(i) * step_len;
         const f3 p = mk3(pos0.x + t * sun.x, pos0.y + t * sun.y, pos0.z + t * sun.z);  // :129, exact
         float inv;
         const float len = sqrt_refined(dot3(p, p), inv);
-        const float dens = cloud_density(c, p, cloud_height_ratio(c, len));
+        const float dens = cloud_density<POW2>(c, p, cloud_height_ratio(c, len));
         if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.density_scale) * -1.4426950408889634f);  // :138-142
         step_len *= 1.2f;                                                                                   // :143
     }
@@ -479,7 +491,10 @@ B200_UNROLL(1)
 }
 
 // raymarch_cloud (:175-247) in model space; returns (total_light, alpha)
+// LIGHT = light mode (bits 0-1) | kLightPow2 (texture sizes are powers of two)
 template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, float t_begin, float t_end, float jitter, f3 sun) {
+    constexpr int MODE = LIGHT & 3;
+    constexpr bool POW2 = (LIGHT & kLightPow2) != 0;
     const int steps = c.cloud_steps;
     // march-length cap (:186-204), exact
     const float max_d = mixf(c.march_ground, c.march_space, smoothstepf(c.march_hmin, c.march_hmax, sqrtf(dot3(o, o))));
@@ -491,7 +506,7 @@ template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, 
 
     // loop invariant: max(pow(dot(ray_dir, sun_dir), 16), 0) (:98-101; a non-positive base gives 0)
     float sunpeek = 0.0f;
-    if (LIGHT == B200ATMO_LIGHT_CHEAP) {
+    if (MODE == B200ATMO_LIGHT_CHEAP) {
         const float dp = dot3(d, sun);
         if (dp > 0.0f) {
             const float p2 = dp * dp, p4 = p2 * p2, p8 = p4 * p4;
@@ -502,15 +517,15 @@ template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, 
     float T_clamped = 1.0f;  // total_transmittance (:222-223)
     float T_alpha = 1.0f;    // 1 - alpha (:228 telescopes to a product of transmittances)
     float total_light = 0.0f;
-B200_UNROLL(1)
+B200_UNROLL(B200ATMO_CLOUD_UNROLL)
     for (int i = 0; i < steps; ++i) {
         float inv;
         const float len = sqrt_refined(dot3(pos, pos), inv);
         const float hr = cloud_height_ratio(c, len);
-        const float dens01 = cloud_density(c, pos, hr);
+        const float dens01 = cloud_density<POW2>(c, pos, hr);
         if (dens01 > 0.0f) {  // density == 0 => transmittance 1, no light added, alpha unchanged: exact skip
             float light;      // get_light (:153-167)
-            if (LIGHT == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched(c, pos, sun, hr);
+            if (MODE == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched<POW2>(c, pos, sun, hr);
             else light = fmaf(sunpeek, T_alpha, hr);                                         // :95-101
             const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);  // dot(normalize(pos), -sun)
             const float st = __saturatef((sdot + 0.3f) * (1.0f / 0.6f));                     // smoothstep(-0.3, 0.3, .) :87
@@ -593,7 +608,7 @@ template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px,
 __device__ __forceinline__ unsigned long long rotr64(unsigned long long v, unsigned s) { return s ? (v >> s) | (v << (64u - s)) : v; }
 __device__ __forceinline__ unsigned long long rotl64(unsigned long long v, unsigned s) { return s ? (v << s) | (v >> (64u - s)) : v; }
 
-__device__ __noinline__ f2 raymarch_cloud_light_queue(const DevConsts& c, const CloudRay r, float jitter, f3 sun, float4* q) {
+template <bool POW2> __device__ __noinline__ f2 raymarch_cloud_light_queue(const DevConsts& c, const CloudRay r, float jitter, f3 sun, float4* q) {
     constexpr unsigned kFull = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     if (!__any_sync(kFull, r.active)) return f2{0.0f, 0.0f};
@@ -617,7 +632,7 @@ __device__ __noinline__ f2 raymarch_cloud_light_queue(const DevConsts& c, const 
         if (lane < n) {
             const unsigned slot = (head + lane) & 63u;
             const float4 a = q[2 * slot];
-            const float L = light_raymarched(c, mk3(a.x, a.y, a.z), sun, a.w);
+            const float L = light_raymarched<POW2>(c, mk3(a.x, a.y, a.z), sun, a.w);
             reinterpret_cast<float*>(q + 2 * slot + 1)[3] = L;
         }
         __syncwarp();
@@ -644,7 +659,7 @@ B200_UNROLL(1)
             float inv;
             const float len = sqrt_refined(dot3(pos, pos), inv);
             hr = cloud_height_ratio(c, len);
-            const float dens01 = cloud_density(c, pos, hr);
+            const float dens01 = cloud_density<POW2>(c, pos, hr);
             if (dens01 > 0.0f) {
                 hit = true;
                 const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);
@@ -768,14 +783,14 @@ template <int MODEL, int LIGHT> B200_DEV bool shade_ray(const DevConsts& c, f3 o
     t_end = fminf(t_end, linear_depth);                            // :162
     if (MODEL == B200ATMO_SCATTER_V1) out = scatter_v1(c, o, d, t_begin, t_end);
     else out = scatter_v2(c, o, d, t_begin, t_end, jitter);
-    if (LIGHT != B200ATMO_LIGHT_NONE) render_clouds<LIGHT>(c, out, o, d, linear_depth, jitter);
+    if ((LIGHT & 3) != B200ATMO_LIGHT_NONE) render_clouds<LIGHT>(c, out, o, d, linear_depth, jitter);
     return false;
 }
 
 #ifdef __CUDACC__
 // shade_ray for the raymarched-light variant with the per-warp light queue: ALL 32 lanes of the warp must call it
 // (`valid` = this lane has a ray); the scatter march and the cloud set-up run per lane, the cloud march cooperatively.
-template <int MODEL> __device__ __forceinline__ bool shade_ray_light_queue(const DevConsts& c, bool valid, f3 o, f3 d, float linear_depth,
+template <int MODEL, bool POW2> __device__ __forceinline__ bool shade_ray_light_queue(const DevConsts& c, bool valid, f3 o, f3 d, float linear_depth,
                                                                          float jitter, float4& out, float4* q) {
     bool disc = true;
     CloudRay cr;
@@ -801,7 +816,7 @@ template <int MODEL> __device__ __forceinline__ bool shade_ray_light_queue(const
         }
     }
     __syncwarp();
-    const f2 rr = raymarch_cloud_light_queue(c, cr, jitter, ld3(c.sun_dir_model), q);
+    const f2 rr = raymarch_cloud_light_queue<POW2>(c, cr, jitter, ld3(c.sun_dir_model), q);
     if (cr.active) clouds_blend(c, out, rr);
     return disc;
 }

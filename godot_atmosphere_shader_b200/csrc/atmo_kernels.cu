@@ -261,11 +261,23 @@ __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float
 // TILED (b200atmo_render_rays_2d): the batch is a c.fw x c.fh pixel grid; a warp covers an 8x4 pixel tile like the frame
 // kernel (four 128-byte segments per load instead of one 512-byte run), so its lanes enter and leave the cloud shell
 // together. A separate instantiation: the linear kernel keeps its code byte for byte.
-#ifdef B200ATMO_MIN_BLOCKS
-#define B200ATMO_RAY_BOUNDS(L) __launch_bounds__(ray_block(L), (L) ? 1 : B200ATMO_MIN_BLOCKS)
+// launch bounds of the ray kernels: scatter-only kernels take B200ATMO_MIN_BLOCKS, cloud kernels B200ATMO_CLOUD_MIN_BLOCKS
+// (tuning knobs; without them ptxas' own register heuristic is used — an explicit minimum of 1 would make it spend 112
+// registers on the cloud kernels)
+template <int L> struct RayBounds {
+#if defined(B200ATMO_CLOUD_MIN_BLOCKS)
+    static constexpr int kCloudMin = B200ATMO_CLOUD_MIN_BLOCKS;
 #else
-#define B200ATMO_RAY_BOUNDS(L) __launch_bounds__(ray_block(L))
+    static constexpr int kCloudMin = 0;
 #endif
+#if defined(B200ATMO_MIN_BLOCKS)
+    static constexpr int kScatterMin = B200ATMO_MIN_BLOCKS;
+#else
+    static constexpr int kScatterMin = 0;
+#endif
+    static constexpr int kMin = L ? kCloudMin : kScatterMin;
+};
+#define B200ATMO_RAY_BOUNDS(L) __launch_bounds__(ray_block(L), RayBounds<L>::kMin)
 template <int MODEL, int LIGHT, class IO, bool TILED>
 __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_constant__ DevConsts c, const IO io) {
     constexpr int BS = ray_block(LIGHT), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;   // block tile = (8*WX) x (4*WY) pixels
@@ -281,7 +293,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
         i = blockIdx.x * size_t(BS) + threadIdx.x;
         valid = i < io.n;
     }
-    if constexpr (LIGHT == B200ATMO_LIGHT_RAYMARCHED && kLightQueue) {
+    if constexpr ((LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED && kLightQueue) {
         // every lane of the warp stays (lanes without a ray are passive): the cloud march is warp-cooperative
         __shared__ float4 s_queue[BS / 32][128];
         float4 od = make_float4(0.f, 0.f, 0.f, 0.f), dj = od, out;
@@ -289,7 +301,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
             od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
             dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
         }
-        const bool disc = shade_ray_light_queue<MODEL>(c, valid, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out,
+        const bool disc = shade_ray_light_queue<MODEL, (LIGHT & kLightPow2) != 0>(c, valid, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out,
                                                         s_queue[threadIdx.x >> 5]);
         if (valid) {
             store_rgba(io, i, out);
@@ -309,7 +321,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
 // Peer variant with TMA bulk stores (RayIOPeers::use_tma): the block's 128 results are staged in shared memory and ONE
 // elected thread sends the 2 KB tile to every rank with cp.async.bulk (shared::cta -> global, the global address being the
 // peer mapping), instead of 128 threads x n_peers STG.128. No thread leaves before the barrier.
-template <int MODEL, int LIGHT>
+template <int MODEL, int LIGHT, int UNUSED>
 __global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_constant__ DevConsts c, const RayIOPeers io) {
     __shared__ __align__(128) float4 s_out[kBlock];   // half4 tiles use the first half of it
     const size_t base = blockIdx.x * size_t(kBlock);
@@ -407,19 +419,30 @@ cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, 
     return cudaGetLastError();
 }
 
-// KERNEL<MODEL, LIGHT, TAIL...>: TAIL = the remaining template arguments (IO type [, TILED])
+// KERNEL<MODEL, LIGHT, TAIL...>: TAIL = the remaining template arguments (IO type). LIGHT = light mode, plus kLightPow2
+// when every texture dimension is a power of two (`light_mode` arrives here already combined: see light_template_arg)
 #define B200ATMO_DISPATCH(KERNEL, GRID, TAIL, ...)                                                            \
     do {                                                                                                     \
-        if (scatter_model == B200ATMO_SCATTER_V1) {                                                           \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<1, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);   \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<1, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<1, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                     \
-        } else {                                                                                             \
-            if (light_mode == B200ATMO_LIGHT_NONE) KERNEL<0, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);   \
-            else if (light_mode == B200ATMO_LIGHT_CHEAP) KERNEL<0, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); \
-            else KERNEL<0, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__);                                     \
+        switch ((scatter_model == B200ATMO_SCATTER_V1 ? 8 : 0) + light_mode) {                                \
+            case 0: KERNEL<0, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 1: KERNEL<0, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 2: KERNEL<0, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 5: KERNEL<0, 5, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 6: KERNEL<0, 6, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 8: KERNEL<1, 0, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 9: KERNEL<1, 1, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                           \
+            case 10: KERNEL<1, 2, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                          \
+            case 13: KERNEL<1, 5, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                          \
+            default: KERNEL<1, 6, TAIL><<<GRID, kBlock, 0, s>>>(__VA_ARGS__); break;                          \
         }                                                                                                    \
     } while (0)
+// light mode of the C-ABI + "all texture dimensions are powers of two" -> the LIGHT template argument
+static int light_template_arg(const DevConsts& c, int light_mode) {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (light_mode == B200ATMO_LIGHT_NONE) return 0;
+    const bool all = pow2(c.cube_res) && pow2(c.shape_nx) && pow2(c.shape_ny) && pow2(c.shape_nz);
+    return light_mode | (all ? kLightPow2 : 0);
+}
 #define B200ATMO_COMMA ,
 
 template <int M, int L, class IO> static void launch_rays_one(const DevConsts& c, const IO& io, cudaStream_t s) {
@@ -433,13 +456,17 @@ template <int M, int L, class IO> static void launch_rays_one(const DevConsts& c
 }
 template <class IO> static cudaError_t launch_rays_t(const DevConsts& c, const IO& io, int scatter_model, int light_mode, cudaStream_t s) {
     if (io.n == 0) return cudaSuccess;
-    switch ((scatter_model == B200ATMO_SCATTER_V1 ? 3 : 0) + light_mode) {
+    switch ((scatter_model == B200ATMO_SCATTER_V1 ? 8 : 0) + light_template_arg(c, light_mode)) {
         case 0: launch_rays_one<0, 0>(c, io, s); break;
         case 1: launch_rays_one<0, 1>(c, io, s); break;
         case 2: launch_rays_one<0, 2>(c, io, s); break;
-        case 3: launch_rays_one<1, 0>(c, io, s); break;
-        case 4: launch_rays_one<1, 1>(c, io, s); break;
-        default: launch_rays_one<1, 2>(c, io, s); break;
+        case 5: launch_rays_one<0, 5>(c, io, s); break;
+        case 6: launch_rays_one<0, 6>(c, io, s); break;
+        case 8: launch_rays_one<1, 0>(c, io, s); break;
+        case 9: launch_rays_one<1, 1>(c, io, s); break;
+        case 10: launch_rays_one<1, 2>(c, io, s); break;
+        case 13: launch_rays_one<1, 5>(c, io, s); break;
+        default: launch_rays_one<1, 6>(c, io, s); break;
     }
     return cudaGetLastError();
 }
@@ -447,6 +474,7 @@ template <class IO> static cudaError_t launch_frame_t(const DevConsts& c, const 
     const int rows = c.row_end - c.row_begin;
     if (rows <= 0 || c.fw <= 0) return cudaSuccess;
     const dim3 grid((c.fw + 15) / 16, (rows + c.row_pitch - 1) / c.row_pitch);   // row_pitch 8: one block row per 8 rows
+    light_mode = light_template_arg(c, light_mode);
     B200ATMO_DISPATCH(render_frame_kernel, grid, IO, c, io);
     return cudaGetLastError();
 }
@@ -457,15 +485,8 @@ cudaError_t launch_render_rays_peers(const DevConsts& c, const RayIOPeers& io, i
     if (!io.use_tma || io.rgba_multicast || c.fw > 0) return launch_rays_t(c, io, scatter_model, light_mode, s);   // the TMA kernel stages LINEAR runs of 128 results
     if (io.n == 0) return cudaSuccess;
     const unsigned grid = unsigned((io.n + kBlock - 1) / kBlock);
-    if (scatter_model == B200ATMO_SCATTER_V1) {
-        if (light_mode == B200ATMO_LIGHT_NONE) render_rays_tma_peers_kernel<1, 0><<<grid, kBlock, 0, s>>>(c, io);
-        else if (light_mode == B200ATMO_LIGHT_CHEAP) render_rays_tma_peers_kernel<1, 1><<<grid, kBlock, 0, s>>>(c, io);
-        else render_rays_tma_peers_kernel<1, 2><<<grid, kBlock, 0, s>>>(c, io);
-    } else {
-        if (light_mode == B200ATMO_LIGHT_NONE) render_rays_tma_peers_kernel<0, 0><<<grid, kBlock, 0, s>>>(c, io);
-        else if (light_mode == B200ATMO_LIGHT_CHEAP) render_rays_tma_peers_kernel<0, 1><<<grid, kBlock, 0, s>>>(c, io);
-        else render_rays_tma_peers_kernel<0, 2><<<grid, kBlock, 0, s>>>(c, io);
-    }
+    light_mode = light_template_arg(c, light_mode);
+    B200ATMO_DISPATCH(render_rays_tma_peers_kernel, grid, 0, c, io);
     return cudaGetLastError();
 }
 cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {

@@ -21,14 +21,14 @@ int density_stage(const DevConsts& c, f3 p, float hr, float& dens) {
     dens = 0.0f;
     const float a = 2.0f * hr - 1.0f;
     const float hc = 1.0f - a * a;
-    if (!(hc > 0.0f)) return 0;
+    if (!(hc > c.hc_min)) return 0;
     const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;
     const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
-    float coverage = sample_cube(c.cube_cells, c.cube_res, cpx, p.y, cpz);
+    float coverage = sample_cube<false>(c.cube_cells, c.cube_res, cpx, p.y, cpz);
     coverage = coverage - 0.25f * hr + c.coverage_bias;
     const float cov_term = mixf(-1.2f, 1.5f, coverage);
     if (!((c.shape_hi_m01 + cov_term) * hc * 50.0f - 20.0f > 0.0f)) return 1;
-    dens = cloud_density(c, p, hr);
+    dens = cloud_density<false>(c, p, hr);
     return dens > 0.0f ? 3 : 2;
 }
 

@@ -49,6 +49,8 @@ static DeviceTextures tex_of(const HostsimTextures* t) {
     }
     d.cube_cells = g_cube.data();
     d.cube_res = t->cube_res;
+    d.cube_max = 0.0f;   // as upload_cube (atmo_capi.cu): the largest texel bounds the cloud density
+    for (size_t i = 0; i < size_t(6) * (t->cube_res + 2) * (t->cube_res + 2); ++i) d.cube_max = t->cube_pad[i] > d.cube_max ? t->cube_pad[i] : d.cube_max;
     d.shape_cells = g_shape.data();
     d.nx = t->nx; d.ny = t->ny; d.nz = t->nz;
     d.blue_noise = t->blue_noise;
@@ -76,14 +78,21 @@ void hostsim_render_rays(const B200AtmoParams* p, const int32_t variant[4], cons
     DevConsts c;
     consts_from_params(c, *p, v, tex_of(t));
     consts_set_frame(c, *p, fr->planet_center_view, fr->sun_center_view, fr->inv_view);
-    const int key = v.scatter_model * 3 + v.light_mode;
+    // like launch_rays_t (atmo_kernels.cu): power-of-two texture sizes select the instantiation with the fused texel coordinates
+    auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+    const bool all_pow2 = pow2(t->cube_res) && pow2(t->nx) && pow2(t->ny) && pow2(t->nz);
+    const int key = v.scatter_model * 8 + (v.light_mode ? (v.light_mode | (all_pow2 ? kLightPow2 : 0)) : 0);
     switch (key) {
         case 0: run_rays<0, 0>(c, od, dj, n, rgba, disc); break;
         case 1: run_rays<0, 1>(c, od, dj, n, rgba, disc); break;
         case 2: run_rays<0, 2>(c, od, dj, n, rgba, disc); break;
-        case 3: run_rays<1, 0>(c, od, dj, n, rgba, disc); break;
-        case 4: run_rays<1, 1>(c, od, dj, n, rgba, disc); break;
-        default: run_rays<1, 2>(c, od, dj, n, rgba, disc); break;
+        case 5: run_rays<0, 5>(c, od, dj, n, rgba, disc); break;
+        case 6: run_rays<0, 6>(c, od, dj, n, rgba, disc); break;
+        case 8: run_rays<1, 0>(c, od, dj, n, rgba, disc); break;
+        case 9: run_rays<1, 1>(c, od, dj, n, rgba, disc); break;
+        case 10: run_rays<1, 2>(c, od, dj, n, rgba, disc); break;
+        case 13: run_rays<1, 5>(c, od, dj, n, rgba, disc); break;
+        default: run_rays<1, 6>(c, od, dj, n, rgba, disc); break;
     }
 }
 

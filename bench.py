@@ -780,10 +780,9 @@ def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
             out[label] = {"unavailable": repr(exc)[:200]}
     out["api"] = "b200atmo_render_rays_peers + symmetric-memory barrier (timed incl. the barrier), double-buffered tiles"
     # NVLink counters of every rank for the headline mode (rank 0 receives, the others send)
-    if nvl is not None:
-        objs = [None] * world
-        dist.all_gather_object(objs, nvl)
-        nvl = {"per_rank": objs}
+    objs = [None] * world
+    dist.all_gather_object(objs, nvl)       # every rank takes part, with or without counters
+    nvl = {"per_rank": objs} if any(o is not None for o in objs) else None
     return out, nvl, fails
 
 

@@ -89,7 +89,8 @@ class B200AtmoPeerTargets(C.Structure):
 
     _fields_ = [("d_rgba_peers", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32), ("d_rgba_multicast", C.c_void_p),
                 ("elem_offset", C.c_uint64), ("first_peer", C.c_int32), ("use_tma", C.c_int32), ("rgba_format", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("n_done_flags", C.c_int32), ("d_done_flags", C.c_void_p * MAX_PEERS), ("done_slot", C.c_int32),
+                ("done_epoch", C.c_uint32)]
 
 
 class B200AtmoNoise(C.Structure):

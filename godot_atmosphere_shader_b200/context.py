@@ -26,6 +26,7 @@ EXPORTS = [
     "b200atmo_render_frame_host_submit", "b200atmo_frame_wait", "b200atmo_render_frame_composite_fmt", "b200atmo_composite_frame_host",
     "b200atmo_render_frame_peers", "b200atmo_render_rays_peers", "b200atmo_render_frame_peers_interleaved",
     "b200atmo_render_rays_2d", "b200atmo_render_frame_fmt", "b200atmo_render_frame_host_fmt", "b200atmo_render_frame_host_submit_fmt",
+    "b200atmo_peers_wait", "b200atmo_peers_signal", "b200atmo_peers_wait_timeouts",
     "b200atmo_launch_count", "b200atmo_table_build_count",
 ]
 
@@ -82,6 +83,9 @@ def lib():
         L.b200atmo_render_frame_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, i32, i32, vp, i32, vp, vp]
         L.b200atmo_render_frame_host_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32, vp]
         L.b200atmo_render_frame_host_submit_fmt.argtypes = [vp, C.POINTER(B200AtmoCamera), vp, i32, i32, vp, i32, vp, i32]
+        L.b200atmo_peers_wait.argtypes = [vp, vp, i32, i32, C.c_uint32, vp]
+        L.b200atmo_peers_signal.argtypes = [vp, C.POINTER(vp), i32, i32, C.c_uint32, vp]
+        L.b200atmo_peers_wait_timeouts.argtypes = [vp]
         for f in ("b200atmo_launch_count", "b200atmo_table_build_count"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = C.c_uint64
@@ -251,6 +255,21 @@ class AtmosphereContext:
     def render_rays_peers(self, frame: B200AtmoFrame, origin_depth, dir_jitter, n, targets, stream=None):
         self._check(lib().b200atmo_render_rays_peers(self._h, C.byref(frame), _dptr(origin_depth), _dptr(dir_jitter), int(n),
                                                      C.byref(targets), stream))
+
+    def peers_wait(self, flags, first_slot, n_slots, epoch, stream=None):
+        """Queue a wait until flags[first_slot : first_slot + n_slots] have all reached `epoch` (b200atmo_peers_wait)."""
+        self._check(lib().b200atmo_peers_wait(self._h, _dptr(flags), int(first_slot), int(n_slots), int(epoch) & 0xFFFFFFFF, stream))
+
+    def peers_signal(self, flag_ptrs, slot, epoch, stream=None):
+        """Queue the publication of `epoch` into element `slot` of every listed flag array (b200atmo_peers_signal)."""
+        arr = (C.c_void_p * len(flag_ptrs))(*[int(q) for q in flag_ptrs])
+        self._check(lib().b200atmo_peers_signal(self._h, arr, len(flag_ptrs), int(slot), int(epoch) & 0xFFFFFFFF, stream))
+
+    def peers_wait_timeouts(self) -> int:
+        rc = lib().b200atmo_peers_wait_timeouts(self._h)
+        if rc < 0:
+            self._check(rc)
+        return rc
 
     def render_frame_host_submit(self, cam: B200AtmoCamera, depth, w, h, rgba, discard=None, slot=0, rgba_format=COLOR_RGBA32F):
         """Pipelined host-buffer frame: returns after enqueueing; `frame_wait(slot)` completes it."""

@@ -68,6 +68,11 @@ struct b200atmo_ctx {
     } tables[kTableStreams];
     uint64_t table_tick = 0;
     uint64_t table_builds = 0;
+    // fused completion signal of the peers kernels: a ring of block counters (zero between launches; each launch takes the
+    // next one, so launches on different streams never share one) and the count of timed-out waits
+    static constexpr int kBlockCounters = 64;
+    unsigned* d_block_counters = nullptr;   // [kBlockCounters] counters + [1] timeouts
+    int next_block_counter = 0;
     uint64_t launches = 0;
     std::string last_error;
 };
@@ -300,6 +305,8 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[0], cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->streams[1], cudaStreamNonBlocking));
     for (auto& sl : ctx->slots) CREATE_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc(&ctx->d_block_counters, sizeof(unsigned) * (b200atmo_ctx::kBlockCounters + 1)));
+    CREATE_TRY(cudaMemset(ctx->d_block_counters, 0, sizeof(unsigned) * (b200atmo_ctx::kBlockCounters + 1)));
 #undef CREATE_TRY
     // unset samplers read as white (README.md:46: "by default they cover the whole atmosphere uniformly")
     const uint8_t white[6] = {255, 255, 255, 255, 255, 255};
@@ -324,6 +331,7 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
     }
     for (auto& ts : ctx->tables)
         for (auto& e : ts.e) cudaFree(e.d);
+    cudaFree(ctx->d_block_counters);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
     cudaFree(ctx->d_lut_cells);
@@ -800,6 +808,20 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     io.rgba_half = t->rgba_format == B200ATMO_COLOR_RGBA16F ? 1 : 0;
     if (io.use_tma && io.rgba_half && (t->elem_offset & 1u))   // cp.async.bulk needs 16-byte aligned destinations
         return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": TMA stores of half4 tiles need an even elem_offset");
+    if (t->n_done_flags < 0 || t->n_done_flags > B200ATMO_MAX_PEERS || t->done_slot < 0)
+        return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": bad completion-flag list");
+    if (t->n_done_flags > 0) {
+        if (io.use_tma) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": the completion signal is not available with use_tma");
+        for (int k = 0; k < t->n_done_flags; ++k) {
+            if (!t->d_done_flags[k]) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL completion-flag array");
+            io.done_flags[k] = static_cast<unsigned*>(t->d_done_flags[k]);
+        }
+        io.n_done_flags = t->n_done_flags;
+        io.done_slot = unsigned(t->done_slot);
+        io.done_epoch = t->done_epoch;
+        io.block_counter = ctx->d_block_counters + ctx->next_block_counter;
+        ctx->next_block_counter = (ctx->next_block_counter + 1) % b200atmo_ctx::kBlockCounters;
+    }
     return B200ATMO_OK;
 }
 
@@ -907,6 +929,40 @@ int b200atmo_frame_wait(b200atmo_ctx* ctx, int slot) {
     sl.in_flight = false;
     CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
     return B200ATMO_OK;
+}
+
+int b200atmo_peers_wait(b200atmo_ctx* ctx, const void* d_flags, int first_slot, int n_slots, uint32_t epoch, void* stream) {
+    if (!ctx || !d_flags) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_peers_wait: NULL argument");
+    if (first_slot < 0 || n_slots < 0 || n_slots > 32) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_peers_wait: bad slot range");
+    if (n_slots == 0) return B200ATMO_OK;
+    DeviceGuard g(ctx->device);
+    CU_TRY(ctx, launch_peers_wait(static_cast<const unsigned*>(d_flags) + first_slot, n_slots, epoch,
+                                  ctx->d_block_counters + b200atmo_ctx::kBlockCounters, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_peers_signal(b200atmo_ctx* ctx, void* const* d_flags_peers, int n_peers, int slot, uint32_t epoch, void* stream) {
+    if (!ctx || !d_flags_peers) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_peers_signal: NULL argument");
+    if (n_peers < 0 || n_peers > B200ATMO_MAX_PEERS || slot < 0) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_peers_signal: bad peer list");
+    if (n_peers == 0) return B200ATMO_OK;
+    PeerFlagList l{};
+    for (int k = 0; k < n_peers; ++k) {
+        if (!d_flags_peers[k]) return fail(ctx, B200ATMO_E_INVALID, "b200atmo_peers_signal: NULL flag array");
+        l.p[k] = static_cast<unsigned*>(d_flags_peers[k]);
+    }
+    DeviceGuard g(ctx->device);
+    CU_TRY(ctx, launch_peers_signal(l, n_peers, unsigned(slot), epoch, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
+int b200atmo_peers_wait_timeouts(b200atmo_ctx* ctx) {
+    if (!ctx) return B200ATMO_E_INVALID;
+    DeviceGuard g(ctx->device);
+    unsigned v = 0;
+    CU_TRY(ctx, cudaMemcpy(&v, ctx->d_block_counters + b200atmo_ctx::kBlockCounters, sizeof(v), cudaMemcpyDeviceToHost));
+    return int(v & 0x7fffffffu);
 }
 
 uint64_t b200atmo_launch_count(const b200atmo_ctx* ctx) { return ctx ? ctx->launches : 0; }

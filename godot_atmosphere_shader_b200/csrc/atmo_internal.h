@@ -99,6 +99,11 @@ struct RayIOPeers : RayIO {
     int use_tma;               // ray kernel: stage the block's results in smem, one cp.async.bulk per peer
     size_t peer_offset;        // pixels (float4 or half4 elements) added to the pixel / ray index in the peer buffers
     int rgba_half;             // tile format on the wire: 0 = float4, 1 = half4 (RTN-even of the fp32 result)
+    // completion signal fused into the kernel (B200AtmoPeerTargets::d_done_flags): the last block to finish publishes `epoch`
+    unsigned* block_counter;   // local scratch, 0 before the launch, reset by the last block; null = no signal
+    unsigned* done_flags[B200ATMO_MAX_PEERS];
+    int n_done_flags;
+    unsigned done_slot, done_epoch;
 };
 
 #ifdef __CUDACC__
@@ -114,6 +119,11 @@ cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter
 cudaError_t launch_render_frame16(const DevConsts& c, const RayIO16& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
 cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, cudaStream_t s);
+cudaError_t launch_peers_wait(const unsigned* d_flags, int n, unsigned epoch, unsigned* d_timeouts, cudaStream_t s);
+struct PeerFlagList {
+    unsigned* p[B200ATMO_MAX_PEERS];
+};
+cudaError_t launch_peers_signal(const PeerFlagList& flags, int n, unsigned slot, unsigned epoch, cudaStream_t s);
 #endif
 
 }  // namespace b200atmo

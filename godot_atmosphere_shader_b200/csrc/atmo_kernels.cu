@@ -257,6 +257,64 @@ __device__ __forceinline__ void store_rgba(const RayIOPeers& io, size_t i, float
     }
 }
 
+// Completion signal of the fused render + delivery kernels: when the LAST block of the grid has stored its pixels, it
+// publishes io.done_epoch into the consumers' flag arrays. Per block: barrier (all stores of the block issued), system
+// fence, one atomic on a local counter; the block that completes the count knows every other block's fence came first
+// (atomics on one location are totally ordered), fences again and releases the flags. All threads of every block must call.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <class IO> __device__ __forceinline__ void peer_done(const IO&) {}
+__device__ __forceinline__ void peer_done(const RayIOPeers& io) {
+    if (!io.block_counter) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(io.block_counter, 1u) == total - 1u) {
+            *io.block_counter = 0u;   // ready for the next launch that is handed this counter
+            __threadfence_system();
+            for (int k = 0; k < io.n_done_flags; ++k) st_release_sys(io.done_flags[k] + io.done_slot, io.done_epoch);
+        }
+    }
+}
+template <class IO> struct IsPeers { static constexpr bool value = false; };
+template <> struct IsPeers<RayIOPeers> { static constexpr bool value = true; };
+
+// One warp: lane k spins until flags[k] has reached `epoch` (signed distance: wrap-around safe), at most ~2 s.
+__global__ void __launch_bounds__(32) peers_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned epoch, unsigned* timeouts) {
+    if (int(threadIdx.x) < n) {
+        const long long t0 = clock64();
+        while (int(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            if (clock64() - t0 > 4000000000ll) {   // a peer died: give up instead of hanging the GPU
+                atomicAdd(timeouts, 1u);
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+__global__ void __launch_bounds__(32) peers_signal_kernel(const PeerFlagList flags, int n, unsigned slot, unsigned epoch) {
+    if (int(threadIdx.x) < n) {
+        __threadfence_system();
+        st_release_sys(flags.p[threadIdx.x] + slot, epoch);
+    }
+}
+cudaError_t launch_peers_wait(const unsigned* d_flags, int n, unsigned epoch, unsigned* d_timeouts, cudaStream_t s) {
+    peers_wait_kernel<<<1, 32, 0, s>>>(d_flags, n, epoch, d_timeouts);
+    return cudaGetLastError();
+}
+cudaError_t launch_peers_signal(const PeerFlagList& flags, int n, unsigned slot, unsigned epoch, cudaStream_t s) {
+    peers_signal_kernel<<<1, 32, 0, s>>>(flags, n, slot, epoch);
+    return cudaGetLastError();
+}
+
 // Ray batch: thread i <-> ray i. Two coalesced LDG.128 in (streaming), one STG.128 out.
 // TILED (b200atmo_render_rays_2d): the batch is a c.fw x c.fh pixel grid; a warp covers an 8x4 pixel tile like the frame
 // kernel (four 128-byte segments per load instead of one 512-byte run), so its lanes enter and leave the cloud shell
@@ -307,15 +365,19 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
             store_rgba(io, i, out);
             if (io.discard) io.discard[i] = disc ? 1 : 0;
         }
+        peer_done(io);
         return;
     }
-    if (!valid) return;
-    const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
-    const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
-    float4 out;
-    const bool disc = shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
-    store_rgba(io, i, out);
-    if (io.discard) io.discard[i] = disc ? 1 : 0;
+    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the completion signal
+    if (valid) {
+        const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
+        const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
+        float4 out;
+        const bool disc = shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
+        store_rgba(io, i, out);
+        if (io.discard) io.discard[i] = disc ? 1 : 0;
+    }
+    peer_done(io);
 }
 
 // Peer variant with TMA bulk stores (RayIOPeers::use_tma): the block's 128 results are staged in shared memory and ONE
@@ -358,11 +420,7 @@ __global__ void B200ATMO_BOUNDS render_rays_tma_peers_kernel(const __grid_consta
 // Frame: a warp covers an 8x4 pixel tile (coherent LUT / texture footprints, full 128 B store
 // segments per tile row), a block of 4 warps a 16x8 tile.
 template <int MODEL, int LIGHT, class IO>
-__global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= c.fw || y >= c.row_end) return;
+__device__ __forceinline__ void frame_pixel(const DevConsts& c, const IO& io, int x, int y) {
     const size_t i = size_t(y) * c.fw + x;
     f3 o, d;
     float linear_depth, jitter;
@@ -393,6 +451,16 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
         store_rgba(io, i, out);
     }
     if (io.discard) io.discard[i] = disc ? 1 : 0;
+}
+template <int MODEL, int LIGHT, class IO>
+__global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = x < c.fw && y < c.row_end;
+    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the completion signal
+    if (valid) frame_pixel<MODEL, LIGHT>(c, io, x, y);
+    peer_done(io);
 }
 
 // Frame front-end only: depth buffer -> SoA rays for the batch API.

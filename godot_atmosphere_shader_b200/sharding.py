@@ -120,20 +120,26 @@ class SymmetricTiles:
     """`depth` x [slots, rays_per_slot, 4] tile buffers per rank in symmetric memory (torch.distributed._symmetric_memory:
     CUDA VMM allocations exchanged between the ranks' processes, plus the NVLS multicast mapping when the fabric has one).
     Rank r's render kernels store slot r straight into the buffers of the ranks that consume it (`targets(rank)`), so
-    after `barrier()` those GPUs hold the tiles: the render is the delivery. PyTorch is the plumbing (allocation,
-    rendezvous, barrier) only.
+    once the frame is complete those GPUs hold the tiles: the render is the delivery. PyTorch is the plumbing (allocation,
+    rendezvous) only.
 
     rgba_format : abi.COLOR_RGBA32F (float4 tiles) or abi.COLOR_RGBA16F (half4 tiles — Godot's own colour-target format,
                   half the NVLink bytes; each channel is the fp32 result rounded to nearest-even).
     root        : None = all-gather (every rank receives every tile); r = deliver-to-root (only rank r's buffer is
                   written: 1/world of the all-gather's fabric traffic).
-    depth       : number of buffers used round-robin, one per frame (`advance()`). With depth >= 2 and ONE barrier per
-                  frame no rank can overwrite a buffer a slower rank is still reading: a rank reaches frame k+2 only after
-                  every rank arrived at the barrier of frame k+1, which each rank queues AFTER its own reads of frame k.
-    All calls of one frame (render, barrier, the consumer's reads) must be queued on the same CUDA stream."""
+    depth       : number of buffers used round-robin, one per frame.
+    sync        : "flags" (default) — the render kernel itself publishes a completion flag into the consumers' flag arrays
+                  when its last block has stored its pixels; consumers wait with b200atmo_peers_wait and publish a
+                  "consumed" flag before their next frame, producers wait for it before they reuse a buffer (credit flow
+                  control): no barrier kernel at all. "barrier" — one symmetric-memory barrier per frame (torch's kernel);
+                  with depth >= 2 that also rules out overwriting a buffer a slower rank still reads.
+    All calls of one frame (render, hand-shake, the consumer's reads) must be queued on the same CUDA stream."""
+
+    DONE_BASE = 0           # flags[DONE_BASE + r]     = last epoch whose pixels producer r has delivered here
+    CONSUMED_BASE = 8       # flags[CONSUMED_BASE + r] = last epoch consumer r has finished reading (published to the producers)
 
     def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False, stagger: bool = True,
-                 use_tma: bool = False, rgba_format: int = 0, root=None, depth: int = 2):
+                 use_tma: bool = False, rgba_format: int = 0, root=None, depth: int = 2, sync: str = "flags"):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -146,6 +152,8 @@ class SymmetricTiles:
         self.rgba_format = int(rgba_format)
         self.root = None if root is None else int(root)
         self.depth = max(1, int(depth))
+        self.sync = "barrier" if self.use_tma else sync      # the TMA flavour has no fused completion signal
+        assert self.sync in ("flags", "barrier")
         group = group if group is not None else dist.group.WORLD
         dtype = torch.float16 if self.rgba_format == COLOR_RGBA16F else torch.float32
         self.tensors, self.handles = [], []
@@ -156,8 +164,16 @@ class SymmetricTiles:
         self.world = self.handles[0].world_size
         self.rank = self.handles[0].rank
         self.cur = 0
+        self.epoch = 0
         self._mc = [int(getattr(hd, "multicast_ptr", 0) or 0) if (use_multicast and self.root is None) else 0 for hd in self.handles]
         self._ptrs = [[int(q) for q in hd.buffer_ptrs] for hd in self.handles]
+        self.flags = symm_mem.empty((16,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self._flag_handle = symm_mem.rendezvous(self.flags, group.group_name)
+        self._flag_ptrs = [int(q) for q in self._flag_handle.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        self._flag_handle.barrier()          # every rank's flags are zero before anyone signals
+        torch.cuda.synchronize(device)
 
     # the buffer of the current frame
     @property
@@ -176,15 +192,31 @@ class SymmetricTiles:
     def buffer_ptrs(self):
         return self._ptrs[self.cur]
 
+    @property
+    def consumers(self):
+        return list(range(self.world)) if self.root is None else [self.root]
+
+    @property
+    def is_consumer(self):
+        return self.root is None or self.rank == self.root
+
     def advance(self):
-        """Switch to the next buffer (call once per frame, before rendering it)."""
+        """Switch to the next buffer (once per frame, before rendering it)."""
         self.cur = (self.cur + 1) % self.depth
 
     def targets(self, slot: int):
         ptrs = self.buffer_ptrs if self.root is None else [self.buffer_ptrs[self.root]]
         first = (self.rank + 1) % self.world if (self.stagger and self.root is None) else 0
-        return peer_targets(ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot, first_peer=first,
-                            use_tma=self.use_tma, rgba_format=self.rgba_format)
+        t = peer_targets(ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot, first_peer=first,
+                         use_tma=self.use_tma, rgba_format=self.rgba_format)
+        if self.sync == "flags":
+            cons = self.consumers
+            for k, r in enumerate(cons):
+                t.d_done_flags[k] = self._flag_ptrs[r]
+            t.n_done_flags = len(cons)
+            t.done_slot = self.DONE_BASE + self.rank
+            t.done_epoch = self.epoch & 0xFFFFFFFF
+        return t
 
     def bytes_sent_per_frame(self, pixels_rendered: int) -> int:
         """NVLink egress of this rank for `pixels_rendered` pixels (stores into its own buffer do not touch the fabric)."""
@@ -193,6 +225,29 @@ class SymmetricTiles:
         if self.root is None:
             return (self.world - 1) * pixels_rendered * px
         return 0 if self.rank == self.root else pixels_rendered * px
+
+    def begin_frame(self, ctx, stream=None):
+        """Next buffer, next epoch; with sync="flags": publish "consumed" for the previous frame (ordered after the reads
+        already queued on `stream`) and wait until the buffer about to be overwritten has been consumed everywhere."""
+        self.advance()
+        self.epoch += 1
+        if self.sync != "flags":
+            return
+        raw = _raw_stream(stream)
+        if self.is_consumer and self.epoch > 1:
+            ctx.peers_signal(self._flag_ptrs, self.CONSUMED_BASE + self.rank, self.epoch - 1, stream=raw)
+        if self.epoch > self.depth:
+            cons = self.consumers
+            ctx.peers_wait(self._flag_ptrs[self.rank], self.CONSUMED_BASE + cons[0], len(cons), self.epoch - self.depth, stream=raw)
+
+    def end_frame(self, ctx, stream=None):
+        """Queue the hand-shake after the render: consumers wait for every producer's completion flag of this epoch
+        (sync="flags"), or all ranks meet in one barrier (sync="barrier")."""
+        if self.sync == "flags":
+            if self.is_consumer:
+                ctx.peers_wait(self._flag_ptrs[self.rank], self.DONE_BASE, self.world, self.epoch, stream=_raw_stream(stream))
+        else:
+            self.barrier(stream)
 
     def barrier(self, stream=None):
         """Stream-ordered inter-rank barrier: after it, every rank's stores have landed here. `stream` = the
@@ -218,18 +273,18 @@ def render_rays_and_gather_fused(ctx, frame, d_origin_depth, d_dir_jitter, n_ray
     `stream`: torch.cuda.Stream or None (current); `grid=(w, h)` selects the tile-mapped ray kernel."""
     if grid is not None:
         raise NotImplementedError("peer stores are implemented for the linear ray mapping and the frame API")
-    tiles.advance()
+    tiles.begin_frame(ctx, stream)
     ctx.render_rays_peers(frame, d_origin_depth, d_dir_jitter, n_rays, tiles.targets(tiles.rank), stream=_raw_stream(stream))
-    tiles.barrier(stream)
+    tiles.end_frame(ctx, stream)
     return tiles.tensor
 
 
 def render_frame_tile_fused(ctx, cam, d_depth, width: int, height: int, tiles: "SymmetricTiles", stream=None):
     """Weak scaling through the FRAME API: this rank's whole width x height tile (its own camera / depth buffer) goes to
     slot `rank` of the consuming ranks' buffers."""
-    tiles.advance()
+    tiles.begin_frame(ctx, stream)
     ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(tiles.rank), stream=_raw_stream(stream))
-    tiles.barrier(stream)
+    tiles.end_frame(ctx, stream)
     return tiles.tensor
 
 
@@ -239,12 +294,12 @@ def render_frame_sharded_fused(ctx, cam, d_depth, width: int, height: int, tiles
     slots=1, rays_per_slot=width*height): rank g renders rows [g*H/G, (g+1)*H/G), or — `interleave` — the 8-row tiles
     g, g+G, g+2G, ... (balanced when the work is not uniform over the frame). Returns the [height, width, 4] view after
     the barrier is queued."""
-    tiles.advance()
+    tiles.begin_frame(ctx, stream)
     if interleave:
         ctx.render_frame_peers_interleaved(cam, d_depth, width, height, tiles.targets(0), tiles.rank, tiles.world,
                                            stream=_raw_stream(stream))
     else:
         b, e = band(height, tiles.rank, tiles.world)
         ctx.render_frame_peers(cam, d_depth, width, height, tiles.targets(0), row_begin=b, row_end=e, stream=_raw_stream(stream))
-    tiles.barrier(stream)
+    tiles.end_frame(ctx, stream)
     return tiles.tensor.view(height, width, 4)

@@ -283,7 +283,12 @@ typedef struct B200AtmoPeerTargets {
     int32_t rgba_format;                    /* B200ATMO_COLOR_RGBA32F (float4 per pixel) or B200ATMO_COLOR_RGBA16F (half4 per pixel,
                                                each channel the fp32 result rounded to nearest-even): the tile format on the wire.
                                                Half the NVLink bytes; elem_offset counts pixels of that format. */
-    int32_t reserved;
+    int32_t n_done_flags;                   /* 0 = no completion signal. Otherwise the render kernel itself publishes `done_epoch` when
+                                               its LAST block has stored its pixels (per-block system fence + atomic block count): */
+    void* d_done_flags[B200ATMO_MAX_PEERS]; /* ... into element `done_slot` of the flag array (uint32_t[]) of every consuming rank, as
+                                               mapped here (symmetric memory). The consumer waits with b200atmo_peers_wait: no     */
+    int32_t done_slot;                      /* barrier kernel, no second pass — render, delivery and hand-shake are ONE kernel.     */
+    uint32_t done_epoch;                    /* Epochs must grow (wrap-around safe); not available with use_tma.                    */
 } B200AtmoPeerTargets;
 /* Delivery patterns are chosen by the pointer list alone: all ranks' mappings = all-gather (every GPU ends with every
  * tile); ONLY the consuming rank's mapping (n_peers = 1) = deliver-to-root (1/world of the fabric traffic of the
@@ -298,6 +303,17 @@ int b200atmo_render_frame_peers_interleaved(b200atmo_ctx* ctx, const B200AtmoCam
                                             int first_tile, int tile_pitch, const B200AtmoPeerTargets* targets, void* stream);
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth,
                                const float* d_dir_jitter, size_t n_rays, const B200AtmoPeerTargets* targets, void* stream);
+/* Hand-shake without a barrier (flags live in symmetric memory, one uint32_t per producer / consumer):
+ *   b200atmo_peers_wait   : queues a one-warp kernel on `stream` that returns when d_flags[first_slot + k] has reached `epoch`
+ *                           for every k < n_slots (acquire at system scope; wrap-around safe). A consumer calls it after its
+ *                           own render: work queued behind it sees every producer's pixels. Producers use it for flow control
+ *                           (wait for the consumer's "consumed" flag before overwriting a buffer).
+ *   b200atmo_peers_signal : queues a kernel that publishes `epoch` into element `slot` of each listed flag array (release at
+ *                           system scope), ordered after everything already queued on `stream` — e.g. "I have consumed frame e".
+ * A wait gives up after ~2 s (a peer died) instead of hanging the GPU; b200atmo_peers_wait_timeouts() counts those. */
+int b200atmo_peers_wait(b200atmo_ctx* ctx, const void* d_flags, int first_slot, int n_slots, uint32_t epoch, void* stream);
+int b200atmo_peers_signal(b200atmo_ctx* ctx, void* const* d_flags_peers, int n_peers, int slot, uint32_t epoch, void* stream);
+int b200atmo_peers_wait_timeouts(b200atmo_ctx* ctx);   /* synchronises the device; >= 0 = number of timed-out waits so far */
 
 /*
  * Pipelined form of b200atmo_render_frame_host for a stream of frames (one per _process tick, or the tiles of an

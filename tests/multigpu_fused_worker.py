@@ -59,19 +59,20 @@ def main():
     oracle_check(ref.view(world, n, 4)[rank].cpu().numpy(), cam, "own tile")
     ref16 = ref.to(torch.float16)    # torch rounds to nearest-even
     for fmt, want in ((abi.COLOR_RGBA32F, ref), (abi.COLOR_RGBA16F, ref16)):
-        for use_mc, use_tma in ((True, False), (False, False), (False, True)):
+        for use_mc, use_tma, sync in ((True, False, "flags"), (False, False, "flags"), (False, False, "barrier"), (False, True, "barrier")):
             for stream in (None, side):
-                tiles = sharding.SymmetricTiles(world, n, dev, use_multicast=use_mc, use_tma=use_tma, rgba_format=fmt)
+                tiles = sharding.SymmetricTiles(world, n, dev, use_multicast=use_mc, use_tma=use_tma, rgba_format=fmt, sync=sync)
                 for t in tiles.tensors:
                     t.fill_(-1.0)
                 torch.cuda.synchronize()
                 dist.barrier()
-                for _ in range(3):   # several frames through the double buffer
+                for _ in range(5):   # several frames through the double buffer (flow control kicks in from the third)
                     out = sharding.render_rays_and_gather_fused(ctx, fr, d_od, d_dj, n, tiles, stream=stream)
                 torch.cuda.synchronize()
                 assert torch.equal(out.view(world * n, 4), want), \
-                    f"rank {rank}: fused tiles differ from render + all-gather (fmt={fmt}, multicast={use_mc}, tma={use_tma})"
-                report[f"gather_f{fmt}_mc{int(use_mc)}_tma{int(use_tma)}"] = bool(tiles.multicast_ptr) if use_mc else True
+                    f"rank {rank}: fused tiles differ from render + all-gather (fmt={fmt}, multicast={use_mc}, tma={use_tma}, sync={sync})"
+                report[f"gather_f{fmt}_mc{int(use_mc)}_tma{int(use_tma)}_{sync}"] = bool(tiles.multicast_ptr) if use_mc else True
+                dist.barrier()
                 del tiles
         # frame API + deliver-to-root: only the root's buffer is written
         root = world - 1
@@ -80,7 +81,10 @@ def main():
             t.fill_(-1.0)
         torch.cuda.synchronize()
         dist.barrier()
-        out = sharding.render_frame_tile_fused(ctx, cam, d_depth, w, h, tiles)
+        for _ in range(4):
+            out = sharding.render_frame_tile_fused(ctx, cam, d_depth, w, h, tiles)
+        torch.cuda.synchronize()
+        dist.barrier()      # non-root ranks do not wait for anyone: let the root finish receiving before checking
         torch.cuda.synchronize()
         if rank == root:
             assert torch.equal(out.view(world * n, 4), want), f"root delivery differs (fmt={fmt})"
@@ -109,8 +113,10 @@ def main():
                         t.fill_(-1.0)
                     torch.cuda.synchronize()
                     dist.barrier()
-                    for _ in range(2):
+                    for _ in range(4):
                         got = sharding.render_frame_sharded_fused(ctx, cam1, d_depth1, w, h, ft, interleave=interleave)
+                    torch.cuda.synchronize()
+                    dist.barrier()
                     torch.cuda.synchronize()
                     if root is None or rank == root:
                         assert torch.equal(got, want), \
@@ -118,6 +124,7 @@ def main():
                     dist.barrier()
                     del ft
     assert len(rows) > 0
+    assert ctx.peers_wait_timeouts() == 0, "a completion-flag wait timed out"
     ctx.close()
     if rank == 0:
         print("FUSED_GATHER_OK", world, report, flush=True)

@@ -170,24 +170,48 @@ class ClockSampler:
 
 
 def nvlink_counters(index):
-    """NVML NVLink data counters of one GPU, summed over its links, in bytes: {"tx": .., "rx": ..} or None."""
+    """NVLink data counters of one GPU, summed over its links, in bytes: {"tx": .., "rx": .., "how": ..}, or {"error": ..}.
+    NVML field values (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX, KiB) with the all-links scope, else per link, else
+    `nvidia-smi nvlink -gt d`."""
+    why = []
     try:
         import pynvml as nv
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(index)
-        tx_id = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
-        rx_id = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)
-        vals = nv.nvmlDeviceGetFieldValues(h, [(tx_id, 0xFFFFFFFF), (rx_id, 0xFFFFFFFF)])   # scope UINT_MAX = all links
-        out = {}
-        for name, v in zip(("tx", "rx"), vals):
-            if v.nvmlReturn != 0:
-                return None
-            vt = v.valueType
-            val = {0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(vt, v.value.ullVal)
-            out[name] = int(val) * 1024   # KiB
-        return out
-    except Exception:
-        return None
+        ids = (getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138), getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139))
+
+        def val(v):
+            u = v.value
+            return int({0: u.dVal, 1: u.uiVal, 2: u.ulVal, 3: u.ullVal, 4: u.sllVal}.get(int(v.valueType), u.ullVal))
+
+        vals = nv.nvmlDeviceGetFieldValues(h, [(ids[0], 0xFFFFFFFF), (ids[1], 0xFFFFFFFF)])
+        if all(int(v.nvmlReturn) == 0 for v in vals):
+            return {"tx": val(vals[0]) * 1024, "rx": val(vals[1]) * 1024, "how": "NVML field values, all-links scope (KiB)"}
+        why.append("all-links scope: nvmlReturn " + str([int(v.nvmlReturn) for v in vals]))
+        tot, links = [0, 0], 0
+        for link in range(18):
+            vals = nv.nvmlDeviceGetFieldValues(h, [(ids[0], link), (ids[1], link)])
+            if all(int(v.nvmlReturn) == 0 for v in vals):
+                tot[0] += val(vals[0])
+                tot[1] += val(vals[1])
+                links += 1
+        if links:
+            return {"tx": tot[0] * 1024, "rx": tot[1] * 1024, "how": f"NVML field values summed over {links} links (KiB)"}
+        why.append("per-link scope: no link answered")
+    except Exception as exc:
+        why.append("NVML: " + repr(exc)[:120])
+    try:
+        import re
+        import subprocess
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+        if tx or rx:
+            return {"tx": tx * 1024, "rx": rx * 1024, "how": "nvidia-smi nvlink -gt d (KiB, summed over links)"}
+        why.append("nvidia-smi nvlink -gt d: no counters in the output: " + txt[:120].replace("\n", " | "))
+    except Exception as exc:
+        why.append("nvidia-smi: " + repr(exc)[:120])
+    return {"error": "; ".join(why)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -768,14 +792,16 @@ def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
             out[label] = {"ms_per_step": ms, "value": world * R.ray_steps / (ms * 1e-3), "tiles_match_nccl": ok,
                           "bytes_in_on_consumer_per_step": (world - 1) * n_rays * px,
                           "consumer_ingress_GBps": (world - 1) * n_rays * px / (ms * 1e-3) / 1e9}
-            if c0 and c1:
+            if c0 is not None and c1 is not None and ("error" in c0 or "error" in c1):
+                nvl = {"mode": label, "gpu": dev.index, "unavailable": c0.get("error") or c1.get("error")}
+            elif c0 and c1:
                 # per timed_ms call: 3 warm-ups + `steps` timed launches
                 per = 3 + steps
                 nvl = {"mode": label, "gpu": dev.index, "launches_between_reads": per,
                        "tx_bytes_per_step": (c1["tx"] - c0["tx"]) / per, "rx_bytes_per_step": (c1["rx"] - c0["rx"]) / per,
                        "algorithmic_tx_bytes_per_step": tiles.bytes_sent_per_frame(n_rays),
                        "algorithmic_rx_bytes_per_step": (world - 1) * n_rays * px if rank == 0 else 0,
-                       "source": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX (all links of this GPU), read around the timed loop"}
+                       "source": c1.get("how", "") + ", read around the timed loop"}
             del tiles
         except Exception as exc:  # symmetric memory unavailable (no P2P / driver support): report, do not fail the bench
             out[label] = {"unavailable": repr(exc)[:200]}

@@ -84,13 +84,22 @@ class B200AtmoCamera(C.Structure):
 MAX_PEERS = 8
 
 
+class B200AtmoPeerSync(C.Structure):
+    """Hand-shake carried out by the render kernel itself (include/b200atmo.h)."""
+
+    _fields_ = [("d_done_flags", C.c_void_p * MAX_PEERS), ("n_done_flags", C.c_int32), ("done_slot", C.c_int32), ("epoch", C.c_uint32),
+                ("credit_epoch", C.c_uint32), ("d_credit_flags", C.c_void_p), ("credit_first_slot", C.c_int32), ("n_credit", C.c_int32),
+                ("d_consumed_flags", C.c_void_p * MAX_PEERS), ("n_consumed_flags", C.c_int32), ("consumed_slot", C.c_int32),
+                ("consumed_epoch", C.c_uint32), ("n_wait", C.c_int32), ("d_wait_flags", C.c_void_p), ("wait_first_slot", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class B200AtmoPeerTargets(C.Structure):
     """Where the fused render + all-gather kernels store: the same symmetric buffer on every rank (include/b200atmo.h)."""
 
     _fields_ = [("d_rgba_peers", C.c_void_p * MAX_PEERS), ("n_peers", C.c_int32), ("d_rgba_multicast", C.c_void_p),
                 ("elem_offset", C.c_uint64), ("first_peer", C.c_int32), ("use_tma", C.c_int32), ("rgba_format", C.c_int32),
-                ("n_done_flags", C.c_int32), ("d_done_flags", C.c_void_p * MAX_PEERS), ("done_slot", C.c_int32),
-                ("done_epoch", C.c_uint32)]
+                ("reserved", C.c_int32), ("sync", B200AtmoPeerSync)]
 
 
 class B200AtmoNoise(C.Structure):

@@ -808,17 +808,21 @@ static int peers_to_io(b200atmo_ctx* ctx, const B200AtmoPeerTargets* t, RayIOPee
     io.rgba_half = t->rgba_format == B200ATMO_COLOR_RGBA16F ? 1 : 0;
     if (io.use_tma && io.rgba_half && (t->elem_offset & 1u))   // cp.async.bulk needs 16-byte aligned destinations
         return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": TMA stores of half4 tiles need an even elem_offset");
-    if (t->n_done_flags < 0 || t->n_done_flags > B200ATMO_MAX_PEERS || t->done_slot < 0)
-        return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": bad completion-flag list");
-    if (t->n_done_flags > 0) {
-        if (io.use_tma) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": the completion signal is not available with use_tma");
-        for (int k = 0; k < t->n_done_flags; ++k) {
-            if (!t->d_done_flags[k]) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL completion-flag array");
-            io.done_flags[k] = static_cast<unsigned*>(t->d_done_flags[k]);
-        }
-        io.n_done_flags = t->n_done_flags;
-        io.done_slot = unsigned(t->done_slot);
-        io.done_epoch = t->done_epoch;
+    const B200AtmoPeerSync& y = t->sync;
+    if (y.n_done_flags < 0 || y.n_done_flags > B200ATMO_MAX_PEERS || y.n_consumed_flags < 0 || y.n_consumed_flags > B200ATMO_MAX_PEERS ||
+        y.n_credit < 0 || y.n_credit > 32 || y.n_wait < 0 || y.n_wait > 32 || y.done_slot < 0 || y.consumed_slot < 0 ||
+        y.credit_first_slot < 0 || y.wait_first_slot < 0)
+        return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": bad hand-shake block");
+    if (y.n_done_flags || y.n_consumed_flags || y.n_credit || y.n_wait) {
+        if (io.use_tma) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": the fused hand-shake is not available with use_tma");
+        for (int k = 0; k < y.n_done_flags; ++k)
+            if (!y.d_done_flags[k]) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL completion-flag array");
+        for (int k = 0; k < y.n_consumed_flags; ++k)
+            if (!y.d_consumed_flags[k]) return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL consumed-flag array");
+        if ((y.n_credit && !y.d_credit_flags) || (y.n_wait && !y.d_wait_flags))
+            return fail(ctx, B200ATMO_E_INVALID, std::string(who) + ": NULL flag array to wait on");
+        io.sync = y;
+        io.timeouts = ctx->d_block_counters + b200atmo_ctx::kBlockCounters;
         io.block_counter = ctx->d_block_counters + ctx->next_block_counter;
         ctx->next_block_counter = (ctx->next_block_counter + 1) % b200atmo_ctx::kBlockCounters;
     }

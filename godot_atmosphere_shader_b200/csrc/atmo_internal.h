@@ -99,11 +99,10 @@ struct RayIOPeers : RayIO {
     int use_tma;               // ray kernel: stage the block's results in smem, one cp.async.bulk per peer
     size_t peer_offset;        // pixels (float4 or half4 elements) added to the pixel / ray index in the peer buffers
     int rgba_half;             // tile format on the wire: 0 = float4, 1 = half4 (RTN-even of the fp32 result)
-    // completion signal fused into the kernel (B200AtmoPeerTargets::d_done_flags): the last block to finish publishes `epoch`
-    unsigned* block_counter;   // local scratch, 0 before the launch, reset by the last block; null = no signal
-    unsigned* done_flags[B200ATMO_MAX_PEERS];
-    int n_done_flags;
-    unsigned done_slot, done_epoch;
+    // hand-shake fused into the kernel (B200AtmoPeerSync)
+    unsigned* block_counter;   // local scratch, 0 before the launch, reset by the last block; null = no hand-shake
+    unsigned* timeouts;        // local counter of waits that gave up
+    B200AtmoPeerSync sync;
 };
 
 #ifdef __CUDACC__

@@ -269,35 +269,59 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// spin until flags[0..n) have all reached `epoch` (signed distance: wrap-around safe); gives up after ~2 s
+__device__ __forceinline__ void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned* timeouts) {
+    const long long t0 = clock64();
+    for (int k = 0; k < n; ++k) {
+        while (int(ld_acquire_sys(flags + k) - epoch) < 0) {
+            if (clock64() - t0 > 4000000000ll) {   // a peer died: do not hang the GPU
+                if (timeouts) atomicAdd(timeouts, 1u);
+                return;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+template <class IO> __device__ __forceinline__ void peer_begin(const IO&) {}
 template <class IO> __device__ __forceinline__ void peer_done(const IO&) {}
+// kernel start: the first block tells the producers which frame this rank has consumed; every block waits for its credit
+__device__ __forceinline__ void peer_begin(const RayIOPeers& io) {
+    if (!io.block_counter) return;
+    const B200AtmoPeerSync& y = io.sync;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0)
+            for (int k = 0; k < y.n_consumed_flags; ++k)
+                st_release_sys(static_cast<unsigned*>(y.d_consumed_flags[k]) + y.consumed_slot, y.consumed_epoch);
+        if (y.n_credit > 0) wait_flags(static_cast<const unsigned*>(y.d_credit_flags) + y.credit_first_slot, y.n_credit, y.credit_epoch, io.timeouts);
+    }
+    if (y.n_credit > 0) __syncthreads();
+}
+// kernel end: per block a barrier (all its stores are issued), a device-scope fence and one atomic on a local counter. The
+// block that completes the count has observed every other block's fence + atomic (device scope), so its own SYSTEM-scope
+// fence orders all of the grid's peer stores before the flags it then releases (causality is transitive across scopes).
+// On a consumer that block finally waits for the producers' flags: the kernel ends when every tile has landed.
 __device__ __forceinline__ void peer_done(const RayIOPeers& io) {
     if (!io.block_counter) return;
+    const B200AtmoPeerSync& y = io.sync;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const unsigned total = gridDim.x * gridDim.y;
         if (atomicAdd(io.block_counter, 1u) == total - 1u) {
             *io.block_counter = 0u;   // ready for the next launch that is handed this counter
             __threadfence_system();
-            for (int k = 0; k < io.n_done_flags; ++k) st_release_sys(io.done_flags[k] + io.done_slot, io.done_epoch);
+            for (int k = 0; k < y.n_done_flags; ++k) st_release_sys(static_cast<unsigned*>(y.d_done_flags[k]) + y.done_slot, y.epoch);
+            if (y.n_wait > 0) wait_flags(static_cast<const unsigned*>(y.d_wait_flags) + y.wait_first_slot, y.n_wait, y.epoch, io.timeouts);
+            __threadfence_system();
         }
     }
 }
 template <class IO> struct IsPeers { static constexpr bool value = false; };
 template <> struct IsPeers<RayIOPeers> { static constexpr bool value = true; };
 
-// One warp: lane k spins until flags[k] has reached `epoch` (signed distance: wrap-around safe), at most ~2 s.
+// Stand-alone wait: one thread spins until flags[0..n) have reached `epoch`.
 __global__ void __launch_bounds__(32) peers_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned epoch, unsigned* timeouts) {
-    if (int(threadIdx.x) < n) {
-        const long long t0 = clock64();
-        while (int(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-            if (clock64() - t0 > 4000000000ll) {   // a peer died: give up instead of hanging the GPU
-                atomicAdd(timeouts, 1u);
-                break;
-            }
-            __nanosleep(100);
-        }
-    }
+    if (threadIdx.x == 0) wait_flags(flags, n, epoch, timeouts);
     __threadfence_system();
 }
 __global__ void __launch_bounds__(32) peers_signal_kernel(const PeerFlagList flags, int n, unsigned slot, unsigned epoch) {
@@ -354,6 +378,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
     if constexpr ((LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED && kLightQueue) {
         // every lane of the warp stays (lanes without a ray are passive): the cloud march is warp-cooperative
         __shared__ float4 s_queue[BS / 32][128];
+        peer_begin(io);
         float4 od = make_float4(0.f, 0.f, 0.f, 0.f), dj = od, out;
         if (valid) {
             od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
@@ -368,7 +393,8 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
         peer_done(io);
         return;
     }
-    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the completion signal
+    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the fused hand-shake
+    peer_begin(io);
     if (valid) {
         const float4 od = __ldcs(static_cast<const float4*>(io.origin_depth) + i);
         const float4 dj = __ldcs(static_cast<const float4*>(io.dir_jitter) + i);
@@ -458,7 +484,8 @@ __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_const
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
     const bool valid = x < c.fw && y < c.row_end;
-    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the completion signal
+    if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the fused hand-shake
+    peer_begin(io);
     if (valid) frame_pixel<MODEL, LIGHT>(c, io, x, y);
     peer_done(io);
 }

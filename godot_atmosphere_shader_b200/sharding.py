@@ -128,11 +128,12 @@ class SymmetricTiles:
     root        : None = all-gather (every rank receives every tile); r = deliver-to-root (only rank r's buffer is
                   written: 1/world of the all-gather's fabric traffic).
     depth       : number of buffers used round-robin, one per frame.
-    sync        : "flags" (default) — the render kernel itself publishes a completion flag into the consumers' flag arrays
-                  when its last block has stored its pixels; consumers wait with b200atmo_peers_wait and publish a
-                  "consumed" flag before their next frame, producers wait for it before they reuse a buffer (credit flow
-                  control): no barrier kernel at all. "barrier" — one symmetric-memory barrier per frame (torch's kernel);
-                  with depth >= 2 that also rules out overwriting a buffer a slower rank still reads.
+    sync        : "flags" (default) — the hand-shake is carried out by the render kernel itself (B200AtmoPeerSync): its last
+                  block publishes a completion flag into the consumers' flag arrays and, on a consumer, waits for the other
+                  producers' flags, so the kernel ends when the frame is complete; its first block publishes "consumed" for
+                  the previous frame and every block waits for that credit before it overwrites a buffer. No barrier, no
+                  extra launch. "barrier" — one symmetric-memory barrier per frame (torch's kernel); with depth >= 2 that
+                  also rules out overwriting a buffer a slower rank still reads.
     All calls of one frame (render, hand-shake, the consumer's reads) must be queued on the same CUDA stream."""
 
     DONE_BASE = 0           # flags[DONE_BASE + r]     = last epoch whose pixels producer r has delivered here
@@ -210,12 +211,28 @@ class SymmetricTiles:
         t = peer_targets(ptrs, self.multicast_ptr, elem_offset=int(slot) * self.rays_per_slot, first_peer=first,
                          use_tma=self.use_tma, rgba_format=self.rgba_format)
         if self.sync == "flags":
+            y, e = t.sync, self.epoch
             cons = self.consumers
-            for k, r in enumerate(cons):
-                t.d_done_flags[k] = self._flag_ptrs[r]
-            t.n_done_flags = len(cons)
-            t.done_slot = self.DONE_BASE + self.rank
-            t.done_epoch = self.epoch & 0xFFFFFFFF
+            for k, r in enumerate(cons):                      # producer: tell every consumer when my pixels have landed
+                y.d_done_flags[k] = self._flag_ptrs[r]
+            y.n_done_flags = len(cons)
+            y.done_slot = self.DONE_BASE + self.rank
+            y.epoch = e & 0xFFFFFFFF
+            if e > self.depth:                                # producer: the buffer I overwrite held frame e - depth
+                y.d_credit_flags = self._flag_ptrs[self.rank]
+                y.credit_first_slot = self.CONSUMED_BASE + cons[0]
+                y.n_credit = len(cons)
+                y.credit_epoch = (e - self.depth) & 0xFFFFFFFF
+            if self.is_consumer:
+                if e > 1:                                     # consumer: everything queued before this kernel has read frame e - 1
+                    for k in range(self.world):
+                        y.d_consumed_flags[k] = self._flag_ptrs[k]
+                    y.n_consumed_flags = self.world
+                    y.consumed_slot = self.CONSUMED_BASE + self.rank
+                    y.consumed_epoch = (e - 1) & 0xFFFFFFFF
+                y.d_wait_flags = self._flag_ptrs[self.rank]   # consumer: the kernel ends when every producer has delivered
+                y.wait_first_slot = self.DONE_BASE
+                y.n_wait = self.world
         return t
 
     def bytes_sent_per_frame(self, pixels_rendered: int) -> int:
@@ -226,27 +243,15 @@ class SymmetricTiles:
             return (self.world - 1) * pixels_rendered * px
         return 0 if self.rank == self.root else pixels_rendered * px
 
-    def begin_frame(self, ctx, stream=None):
-        """Next buffer, next epoch; with sync="flags": publish "consumed" for the previous frame (ordered after the reads
-        already queued on `stream`) and wait until the buffer about to be overwritten has been consumed everywhere."""
+    def begin_frame(self, ctx=None, stream=None):
+        """Next buffer, next epoch (once per frame, before `targets`)."""
         self.advance()
         self.epoch += 1
-        if self.sync != "flags":
-            return
-        raw = _raw_stream(stream)
-        if self.is_consumer and self.epoch > 1:
-            ctx.peers_signal(self._flag_ptrs, self.CONSUMED_BASE + self.rank, self.epoch - 1, stream=raw)
-        if self.epoch > self.depth:
-            cons = self.consumers
-            ctx.peers_wait(self._flag_ptrs[self.rank], self.CONSUMED_BASE + cons[0], len(cons), self.epoch - self.depth, stream=raw)
 
-    def end_frame(self, ctx, stream=None):
-        """Queue the hand-shake after the render: consumers wait for every producer's completion flag of this epoch
-        (sync="flags"), or all ranks meet in one barrier (sync="barrier")."""
-        if self.sync == "flags":
-            if self.is_consumer:
-                ctx.peers_wait(self._flag_ptrs[self.rank], self.DONE_BASE, self.world, self.epoch, stream=_raw_stream(stream))
-        else:
+    def end_frame(self, ctx=None, stream=None):
+        """sync="flags": nothing to queue — the render kernel carried the whole hand-shake (B200AtmoPeerSync) and, on a
+        consumer, only completes when every producer's pixels are here. sync="barrier": one inter-rank barrier."""
+        if self.sync != "flags":
             self.barrier(stream)
 
     def barrier(self, stream=None):

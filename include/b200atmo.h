@@ -269,6 +269,37 @@ int b200atmo_render_frame_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, cons
  * inter-rank barrier that follows the kernels (e.g. the symmetric-memory handle's barrier). No discard mask.
  */
 #define B200ATMO_MAX_PEERS 8
+/*
+ * Hand-shake of the fused render + delivery, carried out BY THE RENDER KERNEL (no barrier kernel, no extra launch). Flags are
+ * uint32_t epochs in symmetric memory (one array per rank, mapped everywhere); epochs grow by one per frame (wrap-around safe).
+ *   producer : the kernel's LAST block to finish (per-block fence + atomic block count) publishes `epoch` into element
+ *              `done_slot` of every listed consumer flag array            -> "my pixels of frame `epoch` have landed"
+ *              every block first waits until d_credit_flags[credit_first_slot .. +n_credit) have reached credit_epoch
+ *                                                                         -> "the buffer I am about to overwrite was consumed"
+ *   consumer : the kernel's FIRST block publishes consumed_epoch into element consumed_slot of the listed arrays when the
+ *              kernel starts, i.e. after everything queued before it      -> "I have finished reading frame consumed_epoch"
+ *              the last block then waits until d_wait_flags[wait_first_slot .. +n_wait) have reached `epoch`: the kernel
+ *              only completes when every producer's pixels are here, so work queued behind it may read them.
+ * Any part may be left empty (n_* = 0 / NULL). Waits give up after ~2 s (b200atmo_peers_wait_timeouts).
+ */
+typedef struct B200AtmoPeerSync {
+    void* d_done_flags[B200ATMO_MAX_PEERS];
+    int32_t n_done_flags;
+    int32_t done_slot;
+    uint32_t epoch;
+    uint32_t credit_epoch;
+    const void* d_credit_flags;
+    int32_t credit_first_slot;
+    int32_t n_credit;
+    void* d_consumed_flags[B200ATMO_MAX_PEERS];
+    int32_t n_consumed_flags;
+    int32_t consumed_slot;
+    uint32_t consumed_epoch;
+    int32_t n_wait;
+    const void* d_wait_flags;
+    int32_t wait_first_slot;
+    int32_t reserved;
+} B200AtmoPeerSync;
 typedef struct B200AtmoPeerTargets {
     void* d_rgba_peers[B200ATMO_MAX_PEERS]; /* the symmetric buffer as mapped here, one pointer per rank (own rank included) */
     int32_t n_peers;                        /* 1..B200ATMO_MAX_PEERS */
@@ -283,12 +314,8 @@ typedef struct B200AtmoPeerTargets {
     int32_t rgba_format;                    /* B200ATMO_COLOR_RGBA32F (float4 per pixel) or B200ATMO_COLOR_RGBA16F (half4 per pixel,
                                                each channel the fp32 result rounded to nearest-even): the tile format on the wire.
                                                Half the NVLink bytes; elem_offset counts pixels of that format. */
-    int32_t n_done_flags;                   /* 0 = no completion signal. Otherwise the render kernel itself publishes `done_epoch` when
-                                               its LAST block has stored its pixels (per-block system fence + atomic block count): */
-    void* d_done_flags[B200ATMO_MAX_PEERS]; /* ... into element `done_slot` of the flag array (uint32_t[]) of every consuming rank, as
-                                               mapped here (symmetric memory). The consumer waits with b200atmo_peers_wait: no     */
-    int32_t done_slot;                      /* barrier kernel, no second pass — render, delivery and hand-shake are ONE kernel.     */
-    uint32_t done_epoch;                    /* Epochs must grow (wrap-around safe); not available with use_tma.                    */
+    int32_t reserved;
+    B200AtmoPeerSync sync;                  /* hand-shake fused into the kernel (all zero = none: follow the call with a barrier) */
 } B200AtmoPeerTargets;
 /* Delivery patterns are chosen by the pointer list alone: all ranks' mappings = all-gather (every GPU ends with every
  * tile); ONLY the consuming rank's mapping (n_peers = 1) = deliver-to-root (1/world of the fabric traffic of the
@@ -303,7 +330,7 @@ int b200atmo_render_frame_peers_interleaved(b200atmo_ctx* ctx, const B200AtmoCam
                                             int first_tile, int tile_pitch, const B200AtmoPeerTargets* targets, void* stream);
 int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth,
                                const float* d_dir_jitter, size_t n_rays, const B200AtmoPeerTargets* targets, void* stream);
-/* Hand-shake without a barrier (flags live in symmetric memory, one uint32_t per producer / consumer):
+/* The same hand-shake as stand-alone calls (for protocols driven from the host side or mixed with other work):
  *   b200atmo_peers_wait   : queues a one-warp kernel on `stream` that returns when d_flags[first_slot + k] has reached `epoch`
  *                           for every k < n_slots (acquire at system scope; wrap-around safe). A consumer calls it after its
  *                           own render: work queued behind it sees every producer's pixels. Producers use it for flow control

@@ -764,7 +764,7 @@ def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
     gathered16 = gathered.to(torch.float16)
     nvl = None
     modes = [("root_rgba16f", dict(root=0, rgba_format=abi.COLOR_RGBA16F)),
-             ("root_rgba16f_barrier_sync", dict(root=0, rgba_format=abi.COLOR_RGBA16F, sync="barrier")),
+             ("root_rgba16f_fused_handshake", dict(root=0, rgba_format=abi.COLOR_RGBA16F, sync="flags")),
              ("root_fp32", dict(root=0, rgba_format=abi.COLOR_RGBA32F)),
              ("allgather_rgba16f", dict(rgba_format=abi.COLOR_RGBA16F)),
              ("allgather_fp32", dict(rgba_format=abi.COLOR_RGBA32F)),
@@ -805,9 +805,9 @@ def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
             del tiles
         except Exception as exc:  # symmetric memory unavailable (no P2P / driver support): report, do not fail the bench
             out[label] = {"unavailable": repr(exc)[:200]}
-    out["api"] = ("b200atmo_render_rays_peers: the kernel stores into the consumers' symmetric buffers and publishes a completion flag "
-                  "from its last block; consumers queue b200atmo_peers_wait, producers a credit wait before reusing a buffer (timed "
-                  "incl. all of that; *_barrier_sync = one symmetric-memory barrier per step instead); double-buffered tiles")
+    out["api"] = ("b200atmo_render_rays_peers: the kernel stores into the consumers' symmetric buffers; one symmetric-memory barrier "
+                  "per step behind it (timed incl. the barrier); *_fused_handshake = no barrier, the kernel's first / last blocks carry "
+                  "the consumed / credit / done / wait flags themselves (B200AtmoPeerSync); double-buffered tiles")
     if ctx.peers_wait_timeouts():
         fails.append("a completion-flag wait timed out")
     # NVLink counters of every rank for the headline mode (rank 0 receives, the others send)
@@ -853,8 +853,8 @@ def measure_strong(torch, dist, a, rank, world, local_rank, timed_ms):
             R.close()
         except Exception as exc:
             out[name] = {"unavailable": repr(exc)[:200]}
-    out["api"] = ("b200atmo_render_frame_peers[_interleaved] with the fused completion flag + b200atmo_peers_wait on the consumers; "
-                  "ms_per_frame is the max over ranks incl. the hand-shake")
+    out["api"] = ("b200atmo_render_frame_peers[_interleaved] + one symmetric-memory barrier; ms_per_frame is the max over ranks "
+                  "incl. the barrier")
     return out, fails
 
 

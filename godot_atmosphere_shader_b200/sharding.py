@@ -128,19 +128,22 @@ class SymmetricTiles:
     root        : None = all-gather (every rank receives every tile); r = deliver-to-root (only rank r's buffer is
                   written: 1/world of the all-gather's fabric traffic).
     depth       : number of buffers used round-robin, one per frame.
-    sync        : "flags" (default) — the hand-shake is carried out by the render kernel itself (B200AtmoPeerSync): its last
-                  block publishes a completion flag into the consumers' flag arrays and, on a consumer, waits for the other
+    sync        : "barrier" (default) — one symmetric-memory barrier per frame behind the render kernel (torch's kernel, ~14 us
+                  at 2 GPUs); with depth >= 2 it also rules out overwriting a buffer a slower rank still reads.
+                  "flags" — the hand-shake is carried out by the render kernel itself (B200AtmoPeerSync): its last block
+                  publishes a completion flag into the consumers' flag arrays and, on a consumer, waits for the other
                   producers' flags, so the kernel ends when the frame is complete; its first block publishes "consumed" for
                   the previous frame and every block waits for that credit before it overwrites a buffer. No barrier, no
-                  extra launch. "barrier" — one symmetric-memory barrier per frame (torch's kernel); with depth >= 2 that
-                  also rules out overwriting a buffer a slower rank still reads.
+                  extra launch — but every block needs a fence behind its peer stores, which holds its CTA slot for one
+                  NVLink round trip (~2 us): measured 4-24 us SLOWER per frame than the barrier, whose
+                  kernel-boundary drain is free. Kept for loosely coupled producers / consumers that cannot meet in a barrier.
     All calls of one frame (render, hand-shake, the consumer's reads) must be queued on the same CUDA stream."""
 
     DONE_BASE = 0           # flags[DONE_BASE + r]     = last epoch whose pixels producer r has delivered here
     CONSUMED_BASE = 8       # flags[CONSUMED_BASE + r] = last epoch consumer r has finished reading (published to the producers)
 
     def __init__(self, slots: int, rays_per_slot: int, device, group=None, use_multicast: bool = False, stagger: bool = True,
-                 use_tma: bool = False, rgba_format: int = 0, root=None, depth: int = 2, sync: str = "flags"):
+                 use_tma: bool = False, rgba_format: int = 0, root=None, depth: int = 2, sync: str = "barrier"):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem

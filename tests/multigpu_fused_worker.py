@@ -76,7 +76,7 @@ def main():
                 del tiles
         # frame API + deliver-to-root: only the root's buffer is written
         root = world - 1
-        tiles = sharding.SymmetricTiles(world, n, dev, rgba_format=fmt, root=root)
+        tiles = sharding.SymmetricTiles(world, n, dev, rgba_format=fmt, root=root, sync="flags")
         for t in tiles.tensors:
             t.fill_(-1.0)
         torch.cuda.synchronize()
@@ -108,7 +108,8 @@ def main():
                 for root in (None, 0):
                     if use_mc and root is not None:
                         continue
-                    ft = sharding.SymmetricTiles(1, n, dev, use_multicast=use_mc, rgba_format=fmt, root=root)
+                    ft = sharding.SymmetricTiles(1, n, dev, use_multicast=use_mc, rgba_format=fmt, root=root,
+                                                 sync="flags" if interleave else "barrier")
                     for t in ft.tensors:
                         t.fill_(-1.0)
                     torch.cuda.synchronize()

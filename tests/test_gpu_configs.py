@@ -320,3 +320,62 @@ def test_interleaved_row_tiles_reassemble_the_frame(cuda_ctx_factory, world):
     from godot_atmosphere_shader_b200.context import B200AtmoError
     with pytest.raises(B200AtmoError):
         ctx.render_frame_peers_interleaved(cam, d_depth, w, h, t, 3, 3)
+
+
+def test_fused_handshake_and_flag_calls_on_one_gpu(cuda_ctx_factory):
+    """B200AtmoPeerSync on a single GPU (this rank is its own producer and consumer): the render kernel publishes the
+    "consumed" epoch at its start, the completion epoch from its last block, and only ends once the awaited flags are there;
+    b200atmo_peers_signal / b200atmo_peers_wait do the same as stand-alone calls. Pixels are those of the plain call."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    w, h = 200, 121
+    p = scenes.demo_params()
+    _setup(ctx, p, 8, 32, abi.LIGHT_CHEAP)
+    cam = scenes.camera_a(w, h)
+    d_depth = torch.from_numpy(scenes.synth_depth(cam, p, w, h)).cuda()
+    want = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    ctx.render_frame(cam, d_depth, w, h, want, None)
+    flags = torch.zeros(16, dtype=torch.int32, device="cuda")
+    buf = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+    d_od = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    d_dj = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+    fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj)
+    for epoch, api in ((1, "frame"), (2, "rays"), (3, "interleaved")):
+        buf.fill_(-7.0)
+        t = sharding.peer_targets([buf.data_ptr()])
+        y = t.sync
+        y.d_done_flags[0] = flags.data_ptr()
+        y.n_done_flags, y.done_slot, y.epoch = 1, 0, epoch
+        y.d_wait_flags, y.wait_first_slot, y.n_wait = flags.data_ptr(), 0, 1           # wait for my own completion flag
+        if epoch > 1:
+            y.d_consumed_flags[0] = flags.data_ptr()
+            y.n_consumed_flags, y.consumed_slot, y.consumed_epoch = 1, 8, epoch - 1
+            y.d_credit_flags, y.credit_first_slot, y.n_credit, y.credit_epoch = flags.data_ptr(), 8, 1, epoch - 1   # published by block 0 of this very kernel
+        if api == "frame":
+            ctx.render_frame_peers(cam, d_depth, w, h, t)
+        elif api == "rays":
+            ctx.render_rays_peers(fr, d_od, d_dj, h * w, t)
+        else:
+            ctx.render_frame_peers_interleaved(cam, d_depth, w, h, t, 0, 1)
+        torch.cuda.synchronize()
+        f = flags.cpu().numpy()
+        assert f[0] == epoch and f[8] == epoch - 1, (api, f)
+        assert torch.equal(buf, want), api
+    # stand-alone calls: a wait that is already satisfied, then signal -> wait across two streams
+    ctx.peers_wait(flags, 0, 1, 3)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ctx.peers_wait(flags, 3, 2, 7, stream=s2.cuda_stream)                      # blocks s2 until slots 3 and 4 reach 7
+    marker = torch.zeros(1, device="cuda")
+    with torch.cuda.stream(s2):
+        marker.add_(1.0)
+    assert not s2.query()                                                        # still waiting
+    ctx.peers_signal([flags.data_ptr()], 3, 7, stream=s1.cuda_stream)
+    ctx.peers_signal([flags.data_ptr()], 4, 9, stream=s1.cuda_stream)          # 9 >= 7 (epochs only need to be reached)
+    s2.synchronize()
+    assert float(marker.item()) == 1.0 and ctx.peers_wait_timeouts() == 0
+    from godot_atmosphere_shader_b200.context import B200AtmoError
+    bad = sharding.peer_targets([buf.data_ptr()], use_tma=True)
+    bad.sync.d_done_flags[0] = flags.data_ptr()
+    bad.sync.n_done_flags = 1
+    with pytest.raises(B200AtmoError):
+        ctx.render_rays_peers(fr, d_od, d_dj, h * w, bad)

@@ -255,7 +255,9 @@ void PlanetAtmosphereB200::_bind_methods() {
 // the draw: depth read-back -> b200atmo_render_frame_host -> blend_mix -> colour write-back
 // ---------------------------------------------------------------------------------------------------------------
 B200AtmosphereEffect::B200AtmosphereEffect() {
-    set_effect_callback_type(EFFECT_CALLBACK_TYPE_POST_OPAQUE);   // where the transparent atmosphere mesh was drawn
+    // The reference draws its mesh in the TRANSPARENT pass, i.e. after the sky: POST_OPAQUE would run before the sky pass and
+    // the sky would then overwrite every far-plane pixel (the limb against space). PRE_TRANSPARENT = after opaque + sky.
+    set_effect_callback_type(EFFECT_CALLBACK_TYPE_PRE_TRANSPARENT);
     set_access_resolved_depth(true);
 }
 
@@ -268,19 +270,38 @@ void B200AtmosphereEffect::_render_callback(int32_t, RenderData* p_render_data) 
     const Vector2i size = buffers->get_internal_size();
     const int w = size.x, h = size.y;
     // the built-ins the fragment stage consumed (planet_atmosphere_no_clouds.gdshader:13-26)
+    // INV_PROJECTION_MATRIX as shaders see it is NOT cam_projection.inverse(): RenderSceneDataRD::update_ubo multiplies the
+    // camera projection by the depth-correction matrix first (y flipped for Vulkan, reverse-Z, depth remapped to 0..1):
+    //   projection = correction * cam_projection;  inv_projection = projection.inverse()
+    // make_ray (csrc/atmo_device.cuh) builds ndc from the top-left SCREEN_UV and the raw reverse-Z depth, exactly like
+    // planet_atmosphere_main.gdshaderinc:128-132, so it needs that corrected matrix (tests/test_godot_conventions.py).
     float inv_p[16], inv_v[16], view[16];
-    store_colmajor(inv_p, scene->get_cam_projection().inverse());
+    const Projection correction = Projection::create_depth_correction(true);   // flip_y = true; 4.3: reverse-Z + 0..1 remap
+    store_colmajor(inv_p, (correction * scene->get_cam_projection()).inverse());
     store_colmajor(inv_v, scene->get_cam_transform());
     store_colmajor(view, scene->get_cam_transform().affine_inverse());
     const B200AtmoCamera cam = owner_->core()->make_camera(inv_p, inv_v, view);
-    const PackedByteArray depth_bytes = rd->texture_get_data(buffers->get_depth_layer(0), 0);   // R32_SFLOAT, reverse-Z
-    if (depth_bytes.size() != int64_t(w) * h * 4) return;
+    // KNOWN COST: texture_get_data / texture_update are synchronous read-backs on the render thread. They stand in for the
+    // zero-copy path (export the depth / colour images with VK_KHR_external_memory and import them with
+    // cudaImportExternalMemory, then call b200atmo_render_frame_composite_fmt on the device pointers), which needs
+    // RenderingDevice to expose the VkDeviceMemory handles. INTEGRATION.md §2.
+    const PackedByteArray depth_bytes = rd->texture_get_data(buffers->get_depth_layer(0), 0);   // reverse-Z
+    if (depth_bytes.size() != int64_t(w) * h * 4) {
+        // D32_SFLOAT has the memory layout of R32_SFLOAT (4 bytes per texel); D24_UNORM_S8 / D32_SFLOAT_S8 do not
+        UtilityFunctions::push_error(String("PlanetAtmosphereB200: the scene depth buffer is not a 32-bit float format (") +
+                                     String::num_int64(depth_bytes.size()) + String(" bytes for ") + String::num_int64(int64_t(w) * h) +
+                                     String(" pixels); add a depth -> R32F copy pass or select D32_SFLOAT"));
+        return;
+    }
     depth_.resize(size_t(w) * h);
     std::memcpy(depth_.data(), depth_bytes.ptr(), depth_bytes.size());
     // render_mode unshaded + blend_mix (planet_atmosphere_*.gdshader:2) straight into the RGBA16F 3D colour target:
     // depth + colour up, fp32 render + blend on the GPU, colour down (b200atmo_composite_frame_host)
     PackedByteArray color = rd->texture_get_data(buffers->get_color_layer(0), 0);
-    if (color.size() != int64_t(w) * h * 8) return;
+    if (color.size() != int64_t(w) * h * 8) {
+        UtilityFunctions::push_error(String("PlanetAtmosphereB200: the 3D colour target is not RGBA16F"));
+        return;
+    }
     if (owner_->core()->composite_host(cam, depth_.data(), w, h, color.ptrw(), B200ATMO_COLOR_RGBA16F) != B200ATMO_OK) {
         UtilityFunctions::push_error(String(owner_->core()->last_error().c_str()));
         return;

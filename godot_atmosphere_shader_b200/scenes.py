@@ -68,6 +68,30 @@ def perspective_reverse_z(fovy_deg: float, aspect: float, near: float, far: floa
     return P
 
 
+def godot_camera_projection(fovy_deg: float, aspect: float, near: float, far: float) -> np.ndarray:
+    """Godot's Projection::set_perspective (core/math/projection.cpp): the GL-convention camera projection the engine keeps
+    (y up, clip z in [-w, w]) — what RenderSceneData.get_cam_projection() returns to a CompositorEffect."""
+    cot = 1.0 / math.tan(math.radians(fovy_deg) * 0.5)
+    dz = far - near
+    P = np.zeros((4, 4), dtype=np.float64)
+    P[0, 0] = cot / aspect
+    P[1, 1] = cot
+    P[2, 2] = -(far + near) / dz
+    P[3, 2] = -1.0
+    P[2, 3] = -2.0 * near * far / dz
+    return P
+
+
+def godot_depth_correction(flip_y: bool = True, reverse_z: bool = True, remap_z: bool = True) -> np.ndarray:
+    """Godot 4.3 Projection::set_depth_correction: the matrix RenderSceneDataRD::update_ubo multiplies in front of the camera
+    projection before it uploads PROJECTION_MATRIX / INV_PROJECTION_MATRIX (y flip for Vulkan, reverse-Z, z remapped 0..1)."""
+    M = np.eye(4)
+    M[1, 1] = -1.0 if flip_y else 1.0
+    M[2, 2] = (-0.5 if reverse_z else 0.5) if remap_z else (-1.0 if reverse_z else 1.0)
+    M[2, 3] = 0.5 if remap_z else 0.0
+    return M
+
+
 def camera_transform(eye, forward, up=(0.0, 1.0, 0.0)) -> np.ndarray:
     """Camera-to-world transform (= INV_VIEW_MATRIX); the camera looks down its -Z."""
     f = np.asarray(forward, dtype=np.float64)

@@ -5,7 +5,6 @@ that lives on GPU 1 (peer access, the same store path as the multi-process symme
 ncu can replay this kernel (the stores are idempotent), which it cannot do for a multi-rank job.
 usage: ncu --metrics nvltx__bytes.sum,nvltx__bytes_data_user.sum,nvltx__bytes_data_protocol.sum,nvlrx__bytes.sum,gpu__time_duration.sum \\
            -k regex:render_frame_kernel --devices 0 python profiles/nvlink_probe.py"""
-import ctypes as C
 import os
 import sys
 
@@ -26,14 +25,6 @@ remote16 = torch.zeros((h, w, 4), dtype=torch.float16, device="cuda:1")
 probe = torch.ones(4, device="cuda:0")
 remote32.view(-1)[:4].copy_(probe)          # a cross-device copy makes torch enable peer access 0 <-> 1
 torch.cuda.synchronize()
-for name in ("libcudart.so.12", "libcudart.so"):
-    try:
-        rt = C.CDLL(name)
-        rt.cudaSetDevice(0)
-        print("cudaDeviceEnablePeerAccess(1) ->", rt.cudaDeviceEnablePeerAccess(1, 0), "(0 = enabled now, 704 = already enabled)")
-        break
-    except OSError:
-        continue
 local = torch.empty((h, w, 4), dtype=torch.float32, device="cuda:0")
 R.ctx.render_frame(R.cam, R.d_depth, w, h, local, None)
 for fmt, buf in ((abi.COLOR_RGBA32F, remote32), (abi.COLOR_RGBA16F, remote16)):

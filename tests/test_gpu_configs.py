@@ -364,15 +364,21 @@ def test_fused_handshake_and_flag_calls_on_one_gpu(cuda_ctx_factory):
     # stand-alone calls: a wait that is already satisfied, then signal -> wait across two streams
     ctx.peers_wait(flags, 0, 1, 3)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    import time
+    one = torch.ones(1, device="cuda")
+    seen = torch.zeros(1).pin_memory()
+    torch.cuda.synchronize()
     ctx.peers_wait(flags, 3, 2, 7, stream=s2.cuda_stream)                      # blocks s2 until slots 3 and 4 reach 7
-    marker = torch.zeros(1, device="cuda")
     with torch.cuda.stream(s2):
-        marker.add_(1.0)
-    assert not s2.query()                                                        # still waiting
+        seen.copy_(one, non_blocking=True)                                       # lands in host memory only after the wait
+    time.sleep(0.05)
+    assert float(seen[0]) == 0.0, f"the wait did not block: flags = {flags.cpu().numpy()}"
     ctx.peers_signal([flags.data_ptr()], 3, 7, stream=s1.cuda_stream)
+    time.sleep(0.02)
+    assert float(seen[0]) == 0.0                                                 # slot 4 is still behind
     ctx.peers_signal([flags.data_ptr()], 4, 9, stream=s1.cuda_stream)          # 9 >= 7 (epochs only need to be reached)
     s2.synchronize()
-    assert float(marker.item()) == 1.0 and ctx.peers_wait_timeouts() == 0
+    assert float(seen[0]) == 1.0 and ctx.peers_wait_timeouts() == 0
     from godot_atmosphere_shader_b200.context import B200AtmoError
     bad = sharding.peer_targets([buf.data_ptr()], use_tma=True)
     bad.sync.d_done_flags[0] = flags.data_ptr()

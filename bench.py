@@ -635,7 +635,7 @@ def run_ours(a, rank, world, local_rank):
         sub = {}
         for name, swl in (("cfg3", Workload(1920, 1080, 8, 64, 1, "A", "cfg3")), ("cfg3_cloud_deck", Workload(1920, 1080, 8, 64, 1, "C", "cfg3")),
                           ("cfg4", Workload(3840, 2160, 8, 128, 2, "A", "cfg4")), ("cfg4_cloud_deck", Workload(3840, 2160, 8, 128, 2, "C", "cfg4"))):
-            sub[name], fails = measure_sub_config(torch, swl, local_rank, timed_ms)
+            sub[name], fails = measure_sub_config(torch, swl, local_rank, timed_ms, clocks.get("sm_mhz"))
             failures += fails
 
     if rank != 0:
@@ -708,7 +708,7 @@ def run_ours(a, rank, world, local_rank):
     return 1 if failures else 0
 
 
-def measure_sub_config(torch, wl, local_rank, timed_ms):
+def measure_sub_config(torch, wl, local_rank, timed_ms, sm_mhz=None):
     """One cloud workload (BASELINE configs[2] / configs[3]): kernel time of the ray API (linear and tile-mapped) and of
     the frame API, the cloud metrics of SURVEY.md §8(d), a parity sample of the timed buffer."""
     R = Runner(torch, wl, local_rank)
@@ -728,6 +728,15 @@ def measure_sub_config(torch, wl, local_rank, timed_ms):
     evals_per_step = 7 if wl.light == 2 else 1
     peak, _ = load_peaks()
     ach = ALGO_BYTES_PER_RAY * R.n_rays / (best * 1e-3) / 1e9
+    facts = load_ncu_facts(wl.key)
+    issue = None
+    if facts.get("warp_instructions") and sm_mhz:
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        ipeak = sms * 4 * sm_mhz * 1e6
+        iach = facts["warp_instructions"] / (til_ms * 1e-3)
+        issue = {"bound": "issue", "achieved": iach / 1e9, "peak": ipeak / 1e9, "unit": "G warp-instr/s", "frac": iach / ipeak,
+                 "warp_instructions_per_launch": facts["warp_instructions"], "kernel": facts.get("kernel"), "source": facts.get("source"),
+                 "note": "tile-mapped launch (the captured one); peak = SMs x 4 schedulers x SM clock"}
     out = {
         "workload": wl.describe(), "ms_per_step": best, "ms_per_step_linear_mapping": lin_ms, "ms_per_step_tile_mapping": til_ms,
         "ms_per_step_frame_api": frm_ms, "ray_steps_per_sec": R.ray_steps / (best * 1e-3), "mpixels_per_s": R.n_rays / (best * 1e-3) / 1e6,
@@ -737,8 +746,9 @@ def measure_sub_config(torch, wl, local_rank, timed_ms):
         "density_evals_note": (f"rays_marched x {wl.cloud_steps} cloud steps x {evals_per_step} density evaluations per step as the reference "
                                "shader executes them (SURVEY.md §2.1 work table); the kernel skips the ones that are exactly 0"),
         "parity_sample": parity,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "note": "issue-bound: ~180 issued instructions per density evaluation on 12 texel reads that hit L1/L2 (DESIGN.md §5.2)"},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": facts.get("dram_bytes"),
+                     "note": "issue-bound: ~170 issued instructions per density evaluation on 12 texel reads that hit L1/L2 (DESIGN.md §5.2)"},
+        "roofline_issue": issue,
     }
     R.close()
     return out, fails

@@ -337,7 +337,9 @@ int b200atmo_render_rays_peers(b200atmo_ctx* ctx, const B200AtmoFrame* frame, co
  *                           (wait for the consumer's "consumed" flag before overwriting a buffer).
  *   b200atmo_peers_signal : queues a kernel that publishes `epoch` into element `slot` of each listed flag array (release at
  *                           system scope), ordered after everything already queued on `stream` — e.g. "I have consumed frame e".
- * A wait gives up after ~2 s (a peer died) instead of hanging the GPU; b200atmo_peers_wait_timeouts() counts those. */
+ * A wait gives up after ~2 s (a peer died) instead of hanging the GPU; b200atmo_peers_wait_timeouts() counts those.
+ * A wait SPINS ON THE GPU: only wait for flags that another GPU publishes, or that work queued EARLIER on this GPU publishes.
+ * A flag published by a launch queued later on this same GPU may never arrive, because streams can share a hardware queue. */
 int b200atmo_peers_wait(b200atmo_ctx* ctx, const void* d_flags, int first_slot, int n_slots, uint32_t epoch, void* stream);
 int b200atmo_peers_signal(b200atmo_ctx* ctx, void* const* d_flags_peers, int n_peers, int slot, uint32_t epoch, void* stream);
 int b200atmo_peers_wait_timeouts(b200atmo_ctx* ctx);   /* synchronises the device; >= 0 = number of timed-out waits so far */

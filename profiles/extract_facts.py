@@ -27,5 +27,5 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
                 "warp_instructions": int(col("smsp__inst_executed.sum")),
                 "kernel": rows[2][hdr.index("Kernel Name")], "ncu_duration_s": col("gpu__time_duration.sum"),
                 "source": f"profiles/{tag}/prof_{key}.summary.txt" if tag else os.path.basename(rep)}
-json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "roofline_traffic.json"), "w"), indent=1)
+# printed, not written: profiles/roofline_traffic.json (read by bench.py) is keyed by workload and curated by hand from this
 print(json.dumps(out, indent=1))

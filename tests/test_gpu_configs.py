@@ -361,24 +361,20 @@ def test_fused_handshake_and_flag_calls_on_one_gpu(cuda_ctx_factory):
         f = flags.cpu().numpy()
         assert f[0] == epoch and f[8] == epoch - 1, (api, f)
         assert torch.equal(buf, want), api
-    # stand-alone calls: a wait that is already satisfied, then signal -> wait across two streams
-    ctx.peers_wait(flags, 0, 1, 3)
+    # stand-alone calls. Signal first, wait afterwards: a wait kernel spins on the GPU, and a flag that only a LATER launch on
+    # this same GPU publishes may never come (streams can share a hardware queue) — the protocol always waits for flags of
+    # OTHER GPUs or of work queued earlier (include/b200atmo.h); real cross-GPU blocking is covered by tests/test_multigpu_fused.py
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    import time
-    one = torch.ones(1, device="cuda")
-    seen = torch.zeros(1).pin_memory()
-    torch.cuda.synchronize()
-    ctx.peers_wait(flags, 3, 2, 7, stream=s2.cuda_stream)                      # blocks s2 until slots 3 and 4 reach 7
-    with torch.cuda.stream(s2):
-        seen.copy_(one, non_blocking=True)                                       # lands in host memory only after the wait
-    time.sleep(0.05)
-    assert float(seen[0]) == 0.0, f"the wait did not block: flags = {flags.cpu().numpy()}"
-    ctx.peers_signal([flags.data_ptr()], 3, 7, stream=s1.cuda_stream)
-    time.sleep(0.02)
-    assert float(seen[0]) == 0.0                                                 # slot 4 is still behind
-    ctx.peers_signal([flags.data_ptr()], 4, 9, stream=s1.cuda_stream)          # 9 >= 7 (epochs only need to be reached)
+    ctx.peers_wait(flags, 0, 1, 3)                                               # already reached
+    ctx.peers_signal([flags.data_ptr(), flags.data_ptr()], 3, 7, stream=s1.cuda_stream)
+    ctx.peers_signal([flags.data_ptr()], 4, 9, stream=s1.cuda_stream)
+    s1.synchronize()
+    ctx.peers_wait(flags, 3, 2, 7, stream=s2.cuda_stream)                      # 7 >= 7 and 9 >= 7: epochs only need to be reached
+    ctx.peers_wait(flags, 4, 1, 0xFFFFFFF0, stream=s2.cuda_stream)             # wrap-around: 9 is "after" 0xFFFFFFF0
     s2.synchronize()
-    assert float(seen[0]) == 1.0 and ctx.peers_wait_timeouts() == 0
+    f = flags.cpu().numpy()
+    assert f[3] == 7 and f[4] == 9 and f[0] == 3 and f[8] == 2
+    assert ctx.peers_wait_timeouts() == 0
     from godot_atmosphere_shader_b200.context import B200AtmoError
     bad = sharding.peer_targets([buf.data_ptr()], use_tma=True)
     bad.sync.d_done_flags[0] = flags.data_ptr()

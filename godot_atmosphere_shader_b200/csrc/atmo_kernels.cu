@@ -481,8 +481,17 @@ __device__ __forceinline__ void frame_pixel(const DevConsts& c, const IO& io, in
 template <int MODEL, int LIGHT, class IO>
 __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
+    int x, y;
+    if (IsPeers<IO>::value && (LIGHT & 3) == B200ATMO_LIGHT_NONE) {
+        // peer stores of a scatter-only frame are NVLink-bound, not issue-bound: a warp covers 16x2 pixels, so a tile row is one
+        // 256-byte (float4) / 128-byte (half4) run instead of 128 / 64 bytes — the ncu NVLink counters show 19 % / 41 % protocol
+        // bytes on top of the pixels for the 8x4 shape (profiles/r02/nvlink_counters.txt). Same 16x8 block tile, same pixels.
+        x = blockIdx.x * 16 + (lane & 15);
+        y = c.row_begin + blockIdx.y * c.row_pitch + warp * 2 + (lane >> 4);
+    } else {
+        x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+        y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
+    }
     const bool valid = x < c.fw && y < c.row_end;
     if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the fused hand-shake
     peer_begin(io);

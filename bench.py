@@ -572,6 +572,8 @@ def run_ours(a, rank, world, local_rank):
         if "ms_per_step" in headline:
             ms_step = headline["ms_per_step"]
             value = value_delivered = world * ray_steps / (ms_step * 1e-3)
+        else:
+            failures.append(f"the delivery of the tiles could not be measured ({headline}): `value` would be compute-only")
         if not a.no_strong:
             strong, fails = measure_strong(torch, dist, a, rank, world, local_rank, timed_ms)
             failures += fails

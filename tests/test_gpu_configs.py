@@ -291,15 +291,20 @@ def test_blue_noise_window_is_256_whatever_the_texture_size(cuda_ctx_factory):
             ctx.upload_blue_noise(np.zeros(bad, np.uint8))
 
 
+@pytest.mark.parametrize("clouds", [True, False], ids=["clouds", "scatter_only"])
 @pytest.mark.parametrize("world", [1, 3, 8])
-def test_interleaved_row_tiles_reassemble_the_frame(cuda_ctx_factory, world):
+def test_interleaved_row_tiles_reassemble_the_frame(cuda_ctx_factory, world, clouds):
     """b200atmo_render_frame_peers_interleaved: rank g of G renders the 8-row tiles g, g+G, ...; the G launches together
     write every pixel exactly once with the bits of the unsharded frame (height not a multiple of 8, more ranks than
-    some frames have tiles)."""
+    some frames have tiles). The scatter-only peers kernel maps warps to 16x2 pixels, the cloud ones to 8x4: both are checked,
+    in both tile formats."""
     torch = _torch()
     ctx = cuda_ctx_factory()
     p = scenes.demo_params()
-    _setup(ctx, p, 8, 32, abi.LIGHT_CHEAP)
+    if clouds:
+        _setup(ctx, p, 8, 32, abi.LIGHT_CHEAP)
+    else:
+        _setup(ctx, p, 8, 0, abi.LIGHT_NONE)
     for (w, h) in ((200, 121), (64, 20)):
         cam = scenes.camera_a(w, h)
         d_depth = torch.from_numpy(scenes.synth_depth(cam, p, w, h)).cuda()
@@ -317,6 +322,13 @@ def test_interleaved_row_tiles_reassemble_the_frame(cuda_ctx_factory, world):
             assert not changed[np.setdiff1d(np.arange(h), rows)].any()      # only this rank's rows are touched
             seen[rows] += 1
         assert (seen == 1).all() and torch.equal(buf, want)
+        half = torch.full((h, w, 4), -7.0, dtype=torch.float16, device="cuda")
+        t16 = sharding.peer_targets([half.data_ptr()], rgba_format=abi.COLOR_RGBA16F)
+        for g in range(world):
+            ctx.render_frame_peers_interleaved(cam, d_depth, w, h, t16, g, world)
+        ctx.render_frame_peers(cam, d_depth, w, h, sharding.peer_targets([buf.data_ptr()]), row_begin=3, row_end=h - 2)   # a band that is not tile aligned
+        torch.cuda.synchronize()
+        assert torch.equal(half, want.to(torch.float16)) and torch.equal(buf, want)
     from godot_atmosphere_shader_b200.context import B200AtmoError
     with pytest.raises(B200AtmoError):
         ctx.render_frame_peers_interleaved(cam, d_depth, w, h, t, 3, 3)

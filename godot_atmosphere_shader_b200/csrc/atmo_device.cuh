@@ -28,12 +28,12 @@
 #define B200ATMO_SCATTER_UNROLL 8
 #endif
 // unroll factors of the cloud loops, chosen on B200 (profiles/r02/tune_clouds.txt): the 6-step light march by 3 (-2.8 % on
-// cfg4), the cloud march by 2 when the light is cheap (-1.6 % on cfg3) and not at all around the raymarched light
+// cfg4), the cloud march by 4 when the light is cheap (-3.6 % on cfg3) and not at all around the raymarched light
 #ifndef B200ATMO_LIGHT_UNROLL
 #define B200ATMO_LIGHT_UNROLL 3
 #endif
 #ifndef B200ATMO_CLOUD_UNROLL_CHEAP
-#define B200ATMO_CLOUD_UNROLL_CHEAP 2
+#define B200ATMO_CLOUD_UNROLL_CHEAP 4
 #endif
 #ifndef B200ATMO_CLOUD_UNROLL_RM
 #define B200ATMO_CLOUD_UNROLL_RM 1

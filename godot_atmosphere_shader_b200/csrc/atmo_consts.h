@@ -74,6 +74,23 @@ inline float cloud_hc_min(float cube_max, float coverage_bias, float shape_hi_m0
     return flo;
 }
 
+// Largest fp32 y with (y * 50) - 20 <= 0 evaluated like the shader (cloud_funcs:62; both operations round): bisection over
+// the float bits of y in [0, 1] (the expression is monotone in y).
+inline float cloud_dens_y_min() {
+    auto positive = [](float y) { return y * 50.0f - 20.0f > 0.0f; };
+    uint32_t lo = 0u, hi;
+    float fhi = 1.0f, f;
+    std::memcpy(&hi, &fhi, 4);
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        std::memcpy(&f, &mid, 4);
+        if (positive(f)) hi = mid;
+        else lo = mid;
+    }
+    std::memcpy(&f, &lo, 4);
+    return f;
+}
+
 // Uniform-only part (everything that does not depend on the frame).
 inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Variant& v, const DeviceTextures& t) {
     std::memset(&c, 0, sizeof(c));
@@ -127,6 +144,8 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
         c.shape_hi_m01 = shape_hi - 0.2f * 0.5f;
     }
     c.hc_min = cloud_hc_min(t.cube_max, c.coverage_bias, c.shape_hi_m01);
+    c.shape_mix0 = 0.5f * (1.0f - c.shape_factor);       // GLSL mix(0.5, tex, f) = 0.5*(1-f) + tex*f, the first product
+    c.dens_y_min = cloud_dens_y_min();
     c.cube_cells = t.cube_cells;
     c.cube_res = t.cube_res;
     c.shape_cells = t.shape_cells;

@@ -466,10 +466,12 @@ template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, floa
     // Exact early-out before the 3D fetch: the expression below is monotone in `shape` (every op is monotone under
     // round-to-nearest, hc > 0), so if it is <= 0 for the largest possible shape value it is <= 0 for the real one
     // and the clamped density is exactly 0. ~3/4 of the in-shell samples of the demo scene end here.
-    if (!((c.shape_hi_m01 + cov_term) * hc * 50.0f - 20.0f > 0.0f)) return 0.0f;
+    // (c.dens_y_min = the largest y with y*50 - 20 <= 0 in fp32, found on the host: the same decision as evaluating
+    // (..)*hc*50 - 20 > 0 with two instructions less)
+    if (!((c.shape_hi_m01 + cov_term) * hc > c.dens_y_min)) return 0.0f;
     const float tex = sample_shape<POW2>(c.shape_cells, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
                                    p.y * c.shape_scale, p.z * c.shape_scale);
-    float shape = mixf(0.5f, tex, c.shape_factor);                             // :48-50
+    float shape = c.shape_mix0 + tex * c.shape_factor;                         // mix(0.5, tex, factor) :48-50; 0.5*(1-factor) from the host
     if (c.shape_invert) shape = 1.0f - shape;                                  // :57-59
     // detail = 0.5 (CLOUDS_ALWAYS_LOW_QUALITY, main:49) => 0.2*detail = 0.1 (same fp32 product)
     float density = (shape - 0.2f * 0.5f + cov_term) * hc;                     // :61
@@ -477,12 +479,24 @@ template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, floa
     return __saturatef(density);                                               // :64
 }
 
-// get_light_raymarched (:104-151)
-template <bool POW2> B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0) {
+// get_light_raymarched (:104-151). `dens0` = the clamped density at pos0, which the caller has just evaluated (> 0: the light
+// is only needed then). The shader's first light sample (i = 0) sits at pos0 + 0*step*sun_dir = pos0 — exactly, 0*x is +-0 and
+// p + (+-0) == p — and get_density is the function the march itself just called there (:131-136: the quality switch is dead,
+// CLOUDS_ALWAYS_LOW_QUALITY), so its value is dens0 bit for bit: six of the shader's seven density evaluations per lit cloud step
+// remain. B200ATMO_LIGHT_RESAMPLE_FIRST restores the literal seventh (tuning / audit knob).
+template <bool POW2> B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0, float dens0) {
     float step_len = c.light_reach * (1.0f / 6.0f);   // reach * inv_steps
+#ifdef B200ATMO_LIGHT_RESAMPLE_FIRST
     float transm = 1.0f;                               // 1 - alpha
+    constexpr int kFirst = 0;
+#else
+    // i = 0: a = 0 + (1 - tr)(1 - 0)  =>  1 - a = tr                                                       :138-142
+    float transm = ex2_approx(dens0 * (step_len * c.density_scale) * -1.4426950408889634f);
+    step_len *= 1.2f;                                                                                       // :143
+    constexpr int kFirst = 1;
+#endif
 B200_UNROLL(B200ATMO_LIGHT_UNROLL)
-    for (int i = 0; i < 6; ++i) {
+    for (int i = kFirst; i < 6; ++i) {
         const float t = float(i) * step_len;
         const f3 p = mk3(pos0.x + t * sun.x, pos0.y + t * sun.y, pos0.z + t * sun.z);  // :129, exact
         float inv;
@@ -532,7 +546,7 @@ B200_UNROLL(kUnroll)
         const float dens01 = cloud_density<POW2>(c, pos, hr);
         if (dens01 > 0.0f) {  // density == 0 => transmittance 1, no light added, alpha unchanged: exact skip
             float light;      // get_light (:153-167)
-            if (MODE == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched<POW2>(c, pos, sun, hr);
+            if (MODE == B200ATMO_LIGHT_RAYMARCHED) light = light_raymarched<POW2>(c, pos, sun, hr, dens01);
             else light = fmaf(sunpeek, T_alpha, hr);                                         // :95-101
             const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);  // dot(normalize(pos), -sun)
             const float st = __saturatef((sdot + 0.3f) * (1.0f / 0.6f));                     // smoothstep(-0.3, 0.3, .) :87
@@ -608,7 +622,7 @@ template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px,
 // multiplied with); whenever 32 items are queued all 32 lanes pop one each and run the light march at full occupancy,
 // then every lane folds the results of ITS items into its accumulator in queue (= step) order. Per ray the arithmetic
 // and its order are exactly those of raymarch_cloud<RAYMARCHED>: results are bit-identical.
-//   q : 64 ring slots x 2 float4 per warp: {pos.xyz, height_ratio}, {shadow factor, density*step, T_clamped, light (out)}
+//   q : 64 ring slots x 2 float4 per warp: {pos.xyz, height_ratio}, {shadow factor, density*step, T_clamped, density (in) / light (out)}
 // Whether it pays depends on how coherent the lanes of a warp are (profiles/r02/warp_model.txt): measured in
 // profiles/r02/tune_clouds.txt.
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +653,7 @@ template <bool POW2> __device__ __noinline__ f2 raymarch_cloud_light_queue(const
         if (lane < n) {
             const unsigned slot = (head + lane) & 63u;
             const float4 a = q[2 * slot];
-            const float L = light_raymarched<POW2>(c, mk3(a.x, a.y, a.z), sun, a.w);
+            const float L = light_raymarched<POW2>(c, mk3(a.x, a.y, a.z), sun, a.w, reinterpret_cast<const float*>(q + 2 * slot + 1)[3]);
             reinterpret_cast<float*>(q + 2 * slot + 1)[3] = L;
         }
         __syncwarp();
@@ -661,7 +675,7 @@ template <bool POW2> __device__ __noinline__ f2 raymarch_cloud_light_queue(const
 B200_UNROLL(1)
     for (int i = 0; i < steps; ++i) {
         bool hit = false;
-        float hr = 0.0f, sf = 0.0f, ds = 0.0f;
+        float hr = 0.0f, sf = 0.0f, ds = 0.0f, d0 = 0.0f;
         if (r.active) {
             float inv;
             const float len = sqrt_refined(dot3(pos, pos), inv);
@@ -669,6 +683,7 @@ B200_UNROLL(1)
             const float dens01 = cloud_density<POW2>(c, pos, hr);
             if (dens01 > 0.0f) {
                 hit = true;
+                d0 = dens01;
                 const float sdot = -(fmaf(pos.z, sun.z, fmaf(pos.y, sun.y, pos.x * sun.x)) * inv);
                 const float st = __saturatef((sdot + 0.3f) * (1.0f / 0.6f));
                 const float shadow = st * st * fmaf(-2.0f, st, 3.0f);
@@ -684,7 +699,7 @@ B200_UNROLL(1)
             if (hit) {
                 const unsigned slot = (head + count + unsigned(__popc(b & ((1u << lane) - 1u)))) & 63u;
                 q[2 * slot] = make_float4(pos.x, pos.y, pos.z, hr);
-                q[2 * slot + 1] = make_float4(sf, ds, T_clamped, 0.0f);
+                q[2 * slot + 1] = make_float4(sf, ds, T_clamped, d0);   // .w: density in, light out
                 mine |= 1ull << slot;
             }
             count += unsigned(__popc(b));

@@ -49,6 +49,8 @@ struct DevConsts {
     float march_hmin, march_hmax;        // cloud_funcs:191-192
     float light_reach;                   // (top-bottom)*0.15, cloud_funcs:108
     float shape_hi_m01;                  // upper bound of (shape - 0.2*detail) over all texel values, see cloud_density
+    float shape_mix0;                    // 0.5*(1 - u_cloud_shape_factor): the constant term of mix(0.5, tex, factor), cloud_funcs:48-50
+    float dens_y_min;                    // largest y for which y*50 - 20 <= 0 in fp32 (cloud_funcs:62), see cloud_density
     float hc_min;                        // height-curve values <= hc_min cannot give a positive density for ANY coverage / shape texel
                                          // (exact bound from the largest coverage texel, atmo_consts.h: cloud_hc_min); 0 = no bound
     const float4* cube_cells;            // [6][res+1][res+1] bilinear footprints of the seamless padded faces (u8/255 as fp32)

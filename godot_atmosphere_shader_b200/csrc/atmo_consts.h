@@ -91,6 +91,32 @@ inline float cloud_dens_y_min() {
     return f;
 }
 
+// The packed copy the cloud loops read (CloudHot, atmo_internal.h); call after any of its sources changed.
+inline void consts_pack_cloud_hot(DevConsts& c) {
+    CloudHot& h = c.hot;
+    for (int k = 0; k < 3; ++k) h.sun[k] = c.sun_dir_model[k];
+    h.bottom_h = c.cloud_bottom_h;
+    h.inv_thickness = c.inv_cloud_thickness;
+    h.thickness = c.cloud_thickness;
+    h.hc_min = c.hc_min;
+    h.coverage_bias = c.coverage_bias;
+    for (int k = 0; k < 4; ++k) h.rot[k] = c.rot[k];
+    h.shape_hi_m01 = c.shape_hi_m01;
+    h.dens_y_min = c.dens_y_min;
+    h.shape_scale = c.shape_scale;
+    h.shape_factor = c.shape_factor;
+    h.shape_mix0 = c.shape_mix0;
+    h.density_scale = c.density_scale;
+    h.shape_invert = c.shape_invert;
+    h.light_reach = c.light_reach;
+    h.cube_cells = c.cube_cells;
+    h.shape_cells = c.shape_cells;
+    h.cube_res = c.cube_res;
+    h.nx = c.shape_nx;
+    h.ny = c.shape_ny;
+    h.nz = c.shape_nz;
+}
+
 // Uniform-only part (everything that does not depend on the frame).
 inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Variant& v, const DeviceTextures& t) {
     std::memset(&c, 0, sizeof(c));
@@ -157,6 +183,7 @@ inline void consts_from_params(DevConsts& c, const B200AtmoParams& p, const Vari
     c.bn_h = t.bn_h;
     c.scatter_steps = v.scatter_steps;
     c.cloud_steps = v.cloud_steps > 0 ? v.cloud_steps : 1;
+    consts_pack_cloud_hot(c);
 }
 
 // Frame-dependent part: the varyings (planet/sun centre in view space) and INV_VIEW_MATRIX.
@@ -173,6 +200,7 @@ inline void consts_set_frame(DevConsts& c, const B200AtmoParams& p, const float 
     float s4[4];
     hostmath::mat4_mul_vec(c.v2m, c.sun_dir[0], c.sun_dir[1], c.sun_dir[2], 0.0f, s4);  // cloud_funcs:288
     for (int k = 0; k < 3; ++k) c.sun_dir_model[k] = s4[k];
+    consts_pack_cloud_hot(c);
 }
 
 // Frame API: derive the varyings like atmosphere_vertex (main:101-103) and the ray-generation matrices.

@@ -443,7 +443,7 @@ B200_UNROLL(2)
 // ------------------------------------------------------------------------------------------------
 // height_ratio (:36-37, :95-96, :111-112): (|p| - bottom) / (top - bottom)
 B200_DEV float cloud_height_ratio(const DevConsts& c, float len) {
-    return div_refined(len - c.cloud_bottom_h, c.cloud_thickness, c.inv_cloud_thickness);
+    return div_refined(len - c.hot.bottom_h, c.hot.thickness, c.hot.inv_thickness);
 }
 
 // get_density_full (:31-68) with |p| and height_ratio already computed; clamped density in [0,1].
@@ -456,23 +456,23 @@ template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, floa
 #ifdef B200ATMO_NO_HCMIN   // tuning knob: the plain shell test
     if (!(hc > 0.0f)) return 0.0f;
 #else
-    if (!(hc > c.hc_min)) return 0.0f;
+    if (!(hc > c.hot.hc_min)) return 0.0f;
 #endif
-    const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;                         // u_cloud_coverage_rotation * p.xz :43, exact
-    const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
-    float coverage = sample_cube<POW2>(c.cube_cells, c.cube_res, cpx, p.y, cpz);     // :45
-    coverage = minus_quarter(coverage, hr) + c.coverage_bias;                  // :46
+    const float cpx = c.hot.rot[0] * p.x + c.hot.rot[2] * p.z;                 // u_cloud_coverage_rotation * p.xz :43, exact
+    const float cpz = c.hot.rot[1] * p.x + c.hot.rot[3] * p.z;
+    float coverage = sample_cube<POW2>(c.hot.cube_cells, c.hot.cube_res, cpx, p.y, cpz);   // :45
+    coverage = minus_quarter(coverage, hr) + c.hot.coverage_bias;              // :46
     const float cov_term = mixf(-1.2f, 1.5f, coverage);
     // Exact early-out before the 3D fetch: the expression below is monotone in `shape` (every op is monotone under
     // round-to-nearest, hc > 0), so if it is <= 0 for the largest possible shape value it is <= 0 for the real one
     // and the clamped density is exactly 0. ~3/4 of the in-shell samples of the demo scene end here.
     // (c.dens_y_min = the largest y with y*50 - 20 <= 0 in fp32, found on the host: the same decision as evaluating
     // (..)*hc*50 - 20 > 0 with two instructions less)
-    if (!((c.shape_hi_m01 + cov_term) * hc > c.dens_y_min)) return 0.0f;
-    const float tex = sample_shape<POW2>(c.shape_cells, c.shape_nx, c.shape_ny, c.shape_nz, p.x * c.shape_scale,
-                                   p.y * c.shape_scale, p.z * c.shape_scale);
-    float shape = c.shape_mix0 + tex * c.shape_factor;                         // mix(0.5, tex, factor) :48-50; 0.5*(1-factor) from the host
-    if (c.shape_invert) shape = 1.0f - shape;                                  // :57-59
+    if (!((c.hot.shape_hi_m01 + cov_term) * hc > c.hot.dens_y_min)) return 0.0f;
+    const float tex = sample_shape<POW2>(c.hot.shape_cells, c.hot.nx, c.hot.ny, c.hot.nz, p.x * c.hot.shape_scale,
+                                   p.y * c.hot.shape_scale, p.z * c.hot.shape_scale);
+    float shape = c.hot.shape_mix0 + tex * c.hot.shape_factor;                         // mix(0.5, tex, factor) :48-50; 0.5*(1-factor) from the host
+    if (c.hot.shape_invert) shape = 1.0f - shape;                              // :57-59
     // detail = 0.5 (CLOUDS_ALWAYS_LOW_QUALITY, main:49) => 0.2*detail = 0.1 (same fp32 product)
     float density = (shape - 0.2f * 0.5f + cov_term) * hc;                     // :61
     density = density * 50.0f - 20.0f;                                         // :62
@@ -485,13 +485,13 @@ template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, floa
 // CLOUDS_ALWAYS_LOW_QUALITY), so its value is dens0 bit for bit: six of the shader's seven density evaluations per lit cloud step
 // remain. B200ATMO_LIGHT_RESAMPLE_FIRST restores the literal seventh (tuning / audit knob).
 template <bool POW2> B200_DEV float light_raymarched(const DevConsts& c, f3 pos0, f3 sun, float hr0, float dens0) {
-    float step_len = c.light_reach * (1.0f / 6.0f);   // reach * inv_steps
+    float step_len = c.hot.light_reach * (1.0f / 6.0f);   // reach * inv_steps
 #ifdef B200ATMO_LIGHT_RESAMPLE_FIRST
     float transm = 1.0f;                               // 1 - alpha
     constexpr int kFirst = 0;
 #else
     // i = 0: a = 0 + (1 - tr)(1 - 0)  =>  1 - a = tr                                                       :138-142
-    float transm = ex2_approx(dens0 * (step_len * c.density_scale) * -1.4426950408889634f);
+    float transm = ex2_approx(dens0 * (step_len * c.hot.density_scale) * -1.4426950408889634f);
     step_len *= 1.2f;                                                                                       // :143
     constexpr int kFirst = 1;
 #endif
@@ -502,7 +502,7 @@ B200_UNROLL(B200ATMO_LIGHT_UNROLL)
         float inv;
         const float len = sqrt_refined(dot3(p, p), inv);
         const float dens = cloud_density<POW2>(c, p, cloud_height_ratio(c, len));
-        if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.density_scale) * -1.4426950408889634f);  // :138-142
+        if (dens > 0.0f) transm *= ex2_approx(dens * (step_len * c.hot.density_scale) * -1.4426950408889634f);  // :138-142
         step_len *= 1.2f;                                                                                   // :143
     }
     const float alpha = 1.0f - transm;
@@ -534,7 +534,7 @@ template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, 
             sunpeek = p8 * p8;
         }
     }
-    const float k = step_len * c.density_scale;
+    const float k = step_len * c.hot.density_scale;
     float T_clamped = 1.0f;  // total_transmittance (:222-223)
     float T_alpha = 1.0f;    // 1 - alpha (:228 telescopes to a product of transmittances)
     float total_light = 0.0f;
@@ -610,7 +610,7 @@ B200_DEV void clouds_blend(const DevConsts& c, float4& px, f2 rr) {
 template <int LIGHT> B200_DEV void render_clouds(const DevConsts& c, float4& px, f3 o, f3 d, float linear_depth, float jitter) {
     const CloudRay r = clouds_setup(c, o, d, linear_depth);
     if (!r.active) return;
-    clouds_blend(c, px, raymarch_cloud<LIGHT>(c, r.o, r.d, r.t0, r.t1, jitter, ld3(c.sun_dir_model)));
+    clouds_blend(c, px, raymarch_cloud<LIGHT>(c, r.o, r.d, r.t0, r.t1, jitter, ld3(c.hot.sun)));
 }
 
 #ifdef __CUDACC__
@@ -643,7 +643,7 @@ template <bool POW2> __device__ __noinline__ f2 raymarch_cloud_light_queue(const
     const float step_len = (t_end - t_begin) * inv_steps;
     f3 pos = o + jitter * step_len * d + d * t_begin;  // :213, exact
     const f3 dstep = d * step_len;
-    const float k = step_len * c.density_scale;
+    const float k = step_len * c.hot.density_scale;
     float T_clamped = 1.0f, T_alpha = 1.0f, total_light = 0.0f;
     unsigned head = 0, count = 0;       // warp-uniform ring state
     unsigned long long mine = 0;        // ring slots that hold items of this lane
@@ -838,7 +838,7 @@ template <int MODEL, bool POW2> __device__ __forceinline__ bool shade_ray_light_
         }
     }
     __syncwarp();
-    const f2 rr = raymarch_cloud_light_queue<POW2>(c, cr, jitter, ld3(c.sun_dir_model), q);
+    const f2 rr = raymarch_cloud_light_queue<POW2>(c, cr, jitter, ld3(c.hot.sun), q);
     if (cr.active) clouds_blend(c, out, rr);
     return disc;
 }

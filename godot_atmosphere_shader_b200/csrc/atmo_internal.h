@@ -16,6 +16,24 @@ constexpr int kLut = B200ATMO_LUT_SIZE;      // 256
 constexpr int kLutPad = kLut + 2;            // clamp-to-edge apron of one texel on every side
 constexpr int kLutCells = kLut + 1;          // bilinear cells between padded texels: 257 x 257
 
+// The constants of the cloud density evaluation, packed into 16-byte aligned quads in the order the evaluation reads them: the
+// kernels fetch kernel parameters with LDC / LDCU inside the (register-starved) march loops, and ptxas merges adjacent aligned
+// scalars into one 64- or 128-bit load: 17 constant loads per density evaluation become 7 (of ~170 issued instructions).
+// Copies of fields of DevConsts (atmo_consts.h: consts_pack_cloud_hot), appended at its END so no other offset moves.
+struct alignas(16) CloudHot {
+    float sun[3];            // sun_dir_model
+    float bottom_h;          // cloud_bottom_h
+    float inv_thickness, thickness, hc_min, coverage_bias;
+    float rot[4];
+    float shape_hi_m01, dens_y_min, shape_scale, shape_factor;
+    float shape_mix0, density_scale;
+    int shape_invert;
+    float light_reach;
+    const float4* cube_cells;
+    const float4* shape_cells;
+    int cube_res, nx, ny, nz;
+};
+
 // Everything a render kernel needs, passed by value as a __grid_constant__ kernel parameter.
 // Host code (atmo_consts.h) fills it with plain fp32 arithmetic in the shader's op order, no FMA
 // contraction, so per-frame constants are bit-identical to what the shader computes per fragment.
@@ -68,6 +86,7 @@ struct DevConsts {
     float clip_box_half;                   // MODE_FAR proxy cube half edge (0 = fullscreen)
     int row_pitch;                         // frame kernel: rows between the 8-row tiles of consecutive blockIdx.y (8 = contiguous band;
                                            // 8*world = the interleaved multi-GPU shard, b200atmo_render_frame_peers_interleaved)
+    CloudHot hot;                          // see above; keep LAST
 };
 
 struct RayIO {

@@ -24,7 +24,7 @@ int density_stage(const DevConsts& c, f3 p, float hr, float& dens) {
     if (!(hc > c.hc_min)) return 0;
     const float cpx = c.rot[0] * p.x + c.rot[2] * p.z;
     const float cpz = c.rot[1] * p.x + c.rot[3] * p.z;
-    float coverage = sample_cube<false>(c.cube_cells, c.cube_res, cpx, p.y, cpz);
+    float coverage = sample_cube<false>(c.hot.cube_cells, c.hot.cube_res, cpx, p.y, cpz);
     coverage = coverage - 0.25f * hr + c.coverage_bias;
     const float cov_term = mixf(-1.2f, 1.5f, coverage);
     if (!((c.shape_hi_m01 + cov_term) * hc * 50.0f - 20.0f > 0.0f)) return 1;

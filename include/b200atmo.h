@@ -258,15 +258,17 @@ int b200atmo_render_frame_host_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam,
 int b200atmo_render_frame_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
                               int row_end, void* d_rgba, int rgba_format, uint8_t* d_discard, void* stream);
 
-/* ---- multi-GPU: fused render + all-gather over NVLink / NVSwitch peer memory ---------------------------------- */
+/* ---- multi-GPU: fused render + delivery over NVLink / NVSwitch peer memory ------------------------------------- */
 /*
- * The screen-tile shard (one process per GPU, rank g renders rows [g*H/G, (g+1)*H/G) or its own tile) ends with every
- * rank holding every tile. Instead of rendering locally and then all-gathering, these calls make the render kernel store
- * each finished RGBA value directly into EVERY rank's copy of a symmetric buffer (same layout on all GPUs, mapped into
- * this process by CUDA IPC / symmetric memory, e.g. torch.distributed._symmetric_memory): with `d_rgba_multicast` (the
- * NVLS multicast mapping of that buffer) one store per pixel is replicated by the NVSwitch; otherwise one peer-to-peer
- * store per rank. The calls are asynchronous on `stream`; the tiles of the other ranks are complete on this GPU after an
- * inter-rank barrier that follows the kernels (e.g. the symmetric-memory handle's barrier). No discard mask.
+ * The screen-tile shard (one process per GPU; rank g renders its own tile, a row band [g*H/G, (g+1)*H/G) or the 8-row tiles
+ * g, g+G, ... of one frame) ends with the consuming rank(s) holding every pixel. Instead of rendering locally and then
+ * gathering, these calls make the render kernel store each finished pixel directly into the consuming ranks' copies of a
+ * symmetric buffer (same layout on all GPUs, mapped into this process by CUDA IPC / symmetric memory, e.g.
+ * torch.distributed._symmetric_memory): one peer-to-peer store per listed rank, or — with `d_rgba_multicast`, the NVLS
+ * multicast mapping of that buffer — one store that the NVSwitch replicates. The calls are asynchronous on `stream`; the
+ * pixels of the other ranks are complete on a consumer after an inter-rank barrier that follows the kernels (e.g. the
+ * symmetric-memory handle's barrier), or when the kernel returns if it carries the hand-shake itself (B200AtmoPeerSync).
+ * No discard mask. Measured delivery rates: DESIGN.md §7.
  */
 #define B200ATMO_MAX_PEERS 8
 /*

@@ -179,6 +179,9 @@ int b200atmo_generate_noise_cubemap(b200atmo_ctx* ctx, const B200AtmoNoise* nois
 
 /* ---- optical-depth LUT (replaces OpticalDepthBaker, optical_depth_baker.gd:37-85) -------------- */
 #define B200ATMO_LUT_SIZE 256
+/* NB a re-bake (explicit, or implied by the first render call after planet_radius / atmosphere_height / density changed)
+ * rewrites the LUT in place and therefore synchronises the device once — like a texture upload, and unlike every other
+ * render call, it must not happen inside a CUDA graph capture. The reference takes two frames for the same event. */
 int b200atmo_bake_optical_depth(b200atmo_ctx* ctx, void* stream);
 int b200atmo_download_lut(b200atmo_ctx* ctx, float* h_lut256x256);    /* bakes first if stale; synchronises */
 /* Debug/parity: device texture layouts as seen by the kernels. */

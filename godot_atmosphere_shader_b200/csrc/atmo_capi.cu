@@ -61,11 +61,26 @@ struct b200atmo_ctx {
         float inv_proj[16] = {};
         uint64_t tick = 0;
     };
+    // heaviest-first block dispatch of the raymarched-cloud launches (atmo_kernels.cu: block_order_kernel): per stream and launch
+    // geometry the per-block cycle counts of the previous launch and the dispatch order sorted from them. Same ownership rule as
+    // the ray tables: an entry is only touched by work queued on its stream.
+    static constexpr int kOrderEntries = 4;
+    struct OrderEntry {
+        unsigned* d_cost = nullptr;     // [n] + d_order [n] in one allocation
+        unsigned* d_order = nullptr;
+        size_t cap = 0;
+        int kind = 0, w = 0, h = 0, row_begin = 0, row_end = 0, row_pitch = 0, cloud_steps = 0;
+        unsigned n = 0;
+        bool valid = false;             // d_order holds a permutation sorted from a previous launch
+        uint64_t tick = 0;
+    };
     struct TableStream {
         cudaStream_t stream = nullptr;
         bool used = false;
         TableEntry e[kTableEntries];
+        OrderEntry o[kOrderEntries];
     } tables[kTableStreams];
+    bool block_order_enabled = true;    // B200ATMO_BLOCK_ORDER=0 switches it off (A/B measurements)
     uint64_t table_tick = 0;
     uint64_t table_builds = 0;
     // fused completion signal of the peers kernels: a ring of block counters (zero between launches; each launch takes the
@@ -237,6 +252,10 @@ int upload_shape(b200atmo_ctx* ctx, const uint8_t* h, int nx, int ny, int nz, cu
 
 extern "C" {
 
+enum { kOrderFrame = 1, kOrderRays2D = 2, kOrderPeers = 3 };
+static b200atmo_ctx::OrderEntry* block_order_begin(b200atmo_ctx* ctx, cudaStream_t s, int kind, const DevConsts& c, unsigned n, RayIO& io);
+static int block_order_finish(b200atmo_ctx* ctx, b200atmo_ctx::OrderEntry* e, cudaStream_t s);
+
 int b200atmo_version(void) { return B200ATMO_VERSION; }
 size_t b200atmo_sizeof_params(void) { return sizeof(B200AtmoParams); }
 size_t b200atmo_sizeof_frame(void) { return sizeof(B200AtmoFrame); }
@@ -284,6 +303,7 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
     b200atmo_ctx* ctx = new (std::nothrow) b200atmo_ctx();
     if (!ctx) return fail(nullptr, B200ATMO_E_NOMEM, "b200atmo_create: out of host memory");
     ctx->device = cuda_device;
+    if (const char* e = std::getenv("B200ATMO_BLOCK_ORDER")) ctx->block_order_enabled = std::atoi(e) != 0;
     b200atmo_default_params(&ctx->params);
     DeviceGuard g(cuda_device);
     auto bail = [&](int code) {
@@ -329,8 +349,10 @@ void b200atmo_destroy(b200atmo_ctx* ctx) {
         cudaFree(sl.d_rgba);
         cudaFree(sl.d_disc);
     }
-    for (auto& ts : ctx->tables)
+    for (auto& ts : ctx->tables) {
         for (auto& e : ts.e) cudaFree(e.d);
+        for (auto& o : ts.o) cudaFree(o.d_cost);
+    }
     cudaFree(ctx->d_block_counters);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_lut_pad);
@@ -480,9 +502,10 @@ static int render_rays_impl(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const
     io.rgba = d_rgba;
     io.discard = d_discard;
     io.n = n_rays;
+    b200atmo_ctx::OrderEntry* oe = width > 0 ? block_order_begin(ctx, s, kOrderRays2D, c, rays2d_grid_blocks(width, height), io) : nullptr;
     CU_TRY(ctx, launch_render_rays(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
-    return B200ATMO_OK;
+    return block_order_finish(ctx, oe, s);
 }
 
 int b200atmo_render_rays(b200atmo_ctx* ctx, const B200AtmoFrame* frame, const float* d_origin_depth, const float* d_dir_jitter,
@@ -584,6 +607,56 @@ static int frame_tables(b200atmo_ctx* ctx, const DevConsts& c, RayIO& io, cudaSt
     return B200ATMO_OK;
 }
 
+// Heaviest-first block dispatch for a raymarched-cloud launch of `n` blocks with this geometry on stream `s`: hands the kernel
+// the cost slots to fill and, if an earlier launch with the same geometry filled them, the order sorted from those. Returns
+// the entry (call block_order_finish after the launch) or null (not a raymarched launch, switched off, no cache row).
+static b200atmo_ctx::OrderEntry* block_order_begin(b200atmo_ctx* ctx, cudaStream_t s, int kind, const DevConsts& c, unsigned n, RayIO& io) {
+    io.block_order = nullptr;
+    io.block_cost = nullptr;
+    if (!ctx->block_order_enabled || ctx->variant.light_mode != B200ATMO_LIGHT_RAYMARCHED || n < 2u) return nullptr;
+    b200atmo_ctx::TableStream* ts = nullptr;
+    for (auto& t : ctx->tables)
+        if (t.used && t.stream == s) { ts = &t; break; }
+    if (!ts)
+        for (auto& t : ctx->tables)
+            if (!t.used) { ts = &t; t.used = true; t.stream = s; break; }
+    if (!ts) return nullptr;
+    b200atmo_ctx::OrderEntry* hit = nullptr;
+    b200atmo_ctx::OrderEntry* lru = &ts->o[0];
+    for (auto& o : ts->o) {
+        if (o.d_cost && o.kind == kind && o.n == n && o.w == c.fw && o.h == c.fh && o.row_begin == c.row_begin && o.row_end == c.row_end &&
+            o.row_pitch == c.row_pitch && o.cloud_steps == c.cloud_steps) { hit = &o; break; }
+        if (o.tick < lru->tick) lru = &o;
+    }
+    if (!hit) {
+        const size_t need = size_t(n) * 2 * sizeof(unsigned);
+        if (lru->cap < need) {
+            if (lru->d_cost && cudaFreeAsync(lru->d_cost, s) != cudaSuccess) return nullptr;
+            lru->d_cost = nullptr;
+            lru->cap = 0;
+            if (cudaMallocAsync(reinterpret_cast<void**>(&lru->d_cost), need, s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            lru->cap = need;
+        }
+        lru->d_order = lru->d_cost + n;
+        if (cudaMemsetAsync(lru->d_cost, 0, size_t(n) * sizeof(unsigned), s) != cudaSuccess) return nullptr;
+        lru->kind = kind; lru->n = n; lru->w = c.fw; lru->h = c.fh; lru->row_begin = c.row_begin; lru->row_end = c.row_end;
+        lru->row_pitch = c.row_pitch; lru->cloud_steps = c.cloud_steps;
+        lru->valid = false;
+        hit = lru;
+    }
+    hit->tick = ++ctx->table_tick;
+    io.block_cost = hit->d_cost;
+    io.block_order = hit->valid ? hit->d_order : nullptr;
+    return hit;
+}
+static int block_order_finish(b200atmo_ctx* ctx, b200atmo_ctx::OrderEntry* e, cudaStream_t s) {
+    if (!e) return B200ATMO_OK;
+    CU_TRY(ctx, launch_block_order(e->d_cost, e->d_order, e->n, s));
+    e->valid = true;
+    ctx->launches++;
+    return B200ATMO_OK;
+}
+
 static bool valid_format(int f) { return f == B200ATMO_COLOR_RGBA32F || f == B200ATMO_COLOR_RGBA16F; }
 static size_t format_bytes(int f) { return f == B200ATMO_COLOR_RGBA16F ? 8 : 16; }
 
@@ -614,9 +687,10 @@ int b200atmo_render_frame_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam, cons
     io.discard = d_discard;
     io.n = size_t(w) * h;
     if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
+    b200atmo_ctx::OrderEntry* oe = block_order_begin(ctx, s, kOrderFrame, c, frame_grid_blocks(c), io);
     CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, s));
     ctx->launches++;
-    return B200ATMO_OK;
+    return block_order_finish(ctx, oe, s);
 }
 
 int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
@@ -776,8 +850,10 @@ int b200atmo_render_frame_host_fmt(b200atmo_ctx* ctx, const B200AtmoCamera* cam,
         c.row_begin = r0;
         c.row_end = r1;
         if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;   // per-stream cache: each band stream has its own copy
+        b200atmo_ctx::OrderEntry* oe = block_order_begin(ctx, s, kOrderFrame, c, frame_grid_blocks(c), io);
         CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, s));
         ctx->launches++;
+        if ((rc = block_order_finish(ctx, oe, s)) != B200ATMO_OK) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(h_out + off * pxb, d_rgba + off * pxb, cnt * pxb, cudaMemcpyDeviceToHost, s));
         if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard + off, ctx->d_stage_disc + off, cnt, cudaMemcpyDeviceToHost, s));
         r0 = r1;
@@ -845,9 +921,10 @@ static int render_frame_peers_impl(b200atmo_ctx* ctx, const B200AtmoCamera* cam,
     io.depth = d_depth;
     io.n = size_t(w) * h;
     if ((rc = frame_tables(ctx, c, io, s)) != B200ATMO_OK) return rc;
+    b200atmo_ctx::OrderEntry* oe = block_order_begin(ctx, s, kOrderPeers, c, frame_grid_blocks(c), io);
     CU_TRY(ctx, launch_render_frame_peers(c, io, ctx->variant.scatter_model, ctx->variant.light_mode, s));
     ctx->launches++;
-    return B200ATMO_OK;
+    return block_order_finish(ctx, oe, s);
 }
 
 int b200atmo_render_frame_peers(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth, int w, int h, int row_begin,
@@ -912,8 +989,10 @@ int b200atmo_render_frame_host_submit_fmt(b200atmo_ctx* ctx, const B200AtmoCamer
     if ((rc = frame_tables(ctx, c, io, sl.stream)) != B200ATMO_OK) return rc;
     sl.in_flight = true;   // from the first enqueue on the host buffers are in use, also if a later enqueue fails
     CU_TRY(ctx, cudaMemcpyAsync(sl.d_depth, h_depth, npx * sizeof(float), cudaMemcpyHostToDevice, sl.stream));
+    b200atmo_ctx::OrderEntry* oe = block_order_begin(ctx, sl.stream, kOrderFrame, c, frame_grid_blocks(c), io);
     CU_TRY(ctx, launch_frame_any(c, io, rgba_format, ctx->variant, sl.stream));
     ctx->launches++;
+    if ((rc = block_order_finish(ctx, oe, sl.stream)) != B200ATMO_OK) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(h_rgba, sl.d_rgba, npx * pxb, cudaMemcpyDeviceToHost, sl.stream));
     if (h_discard) CU_TRY(ctx, cudaMemcpyAsync(h_discard, sl.d_disc, npx, cudaMemcpyDeviceToHost, sl.stream));
     return B200ATMO_OK;

@@ -105,6 +105,10 @@ struct RayIO {
     // ptxas schedule of the march loop depends on them).
     const float4* ray_col;     // [fw]  m[0..3] * ndc.x(x)
     const float4* ray_row;     // [fh]  m[4..7] * ndc.y(y)
+    // raymarched-cloud launches on a 2D block grid: heaviest-first dispatch order learned from the previous launch with the
+    // same geometry (atmo_kernels.cu: block_order_kernel). Null = blockIdx order / nothing recorded.
+    const unsigned* block_order;   // [gridDim.x * gridDim.y] permutation: the k-th dispatched block renders logical block block_order[k]
+    unsigned* block_cost;          // [same] cycles each logical block took (max over its warps) in THIS launch
 };
 // RGBA16F result (b200atmo_render_frame*_fmt): the same fields, a different TYPE, so the store is chosen at compile time and
 // the fp32 kernels keep their code byte for byte. rgba = half4[...].
@@ -139,6 +143,9 @@ cudaError_t launch_render_frame(const DevConsts& c, const RayIO& io, int scatter
 cudaError_t launch_render_frame16(const DevConsts& c, const RayIO16& io, int scatter_model, int light_mode, cudaStream_t s);
 cudaError_t launch_make_rays(const DevConsts& c, const RayIO& io, cudaStream_t s);
 cudaError_t launch_ray_tables(const DevConsts& c, float4* d_col, float4* d_row, cudaStream_t s);
+cudaError_t launch_block_order(unsigned* d_cost, unsigned* d_order, unsigned n, cudaStream_t s);
+unsigned frame_grid_blocks(const DevConsts& c);     // blocks of a frame-kernel launch for rows [c.row_begin, c.row_end) at c.row_pitch
+unsigned rays2d_grid_blocks(int w, int h);          // blocks of a tile-mapped cloud ray-batch launch
 cudaError_t launch_peers_wait(const unsigned* d_flags, int n, unsigned epoch, unsigned* d_timeouts, cudaStream_t s);
 struct PeerFlagList {
     unsigned* p[B200ATMO_MAX_PEERS];

@@ -316,6 +316,60 @@ __device__ __forceinline__ void peer_done(const RayIOPeers& io) {
         }
     }
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Heaviest-first dispatch of the blocks of a raymarched-cloud launch. A block whose rays cross dense cloud lives ~5x longer
+// than the average block (one ray is a serial chain of up to 128 x 6 density evaluations), blocks are dispatched in blockIdx
+// order, and whatever heavy blocks start late finish alone: a list-scheduling model of the 3840x2160 frame on 148 x 9 block slots
+// (profiles/microbench/tail_model.py) puts that tail at +7 % on one GPU and +35 % when the frame is split over 8 — the measured
+// strong-scaling loss — and at +0 % / +3 % when the blocks are dispatched longest first. The costs come from the previous
+// launch with the same geometry on the same stream (frames are temporally coherent): every warp adds its elapsed cycles to its
+// logical block's slot (atomicMax), block_order_kernel then sorts the blocks by cost into `block_order` (counting sort, 256
+// bins, one 1024-thread block) and clears the costs. The k-th dispatched block renders logical block block_order[k]: a
+// permutation of the blocks — pixels are untouched. Only the raymarched-light kernels use it (their blocks are long enough).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned logical_block(const RayIO& io) {
+    unsigned lb = blockIdx.y * gridDim.x + blockIdx.x;
+    if (io.block_order) lb = __ldg(io.block_order + lb);
+    return lb;
+}
+__device__ __forceinline__ void record_block_cost(const RayIO& io, unsigned lb, long long t0) {
+    if (!io.block_cost) return;
+    const unsigned lanes = __activemask();
+    if ((threadIdx.x & 31u) == unsigned(__ffs(int(lanes)) - 1)) {
+        const long long dt = clock64() - t0;
+        atomicMax(io.block_cost + lb, dt > 0xffffffffll ? 0xffffffffu : unsigned(dt));
+    }
+}
+__global__ void __launch_bounds__(1024) block_order_kernel(unsigned* __restrict__ cost, unsigned* __restrict__ order, unsigned n) {
+    __shared__ unsigned s_max, s_hist[256], s_pos[256];
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) s_max = 0u;
+    if (tid < 256u) s_hist[tid] = 0u;
+    __syncthreads();
+    unsigned m = 0u;
+    for (unsigned i = tid; i < n; i += 1024u) m = max(m, cost[i]);
+    atomicMax(&s_max, m);
+    __syncthreads();
+    const unsigned long long mx = s_max ? s_max : 1u;
+    for (unsigned i = tid; i < n; i += 1024u) atomicAdd(&s_hist[255u - unsigned(cost[i] * 255ull / mx)], 1u);   // bin 0 = the heaviest
+    __syncthreads();
+    if (tid == 0) {
+        unsigned acc = 0u;
+        for (int b = 0; b < 256; ++b) {
+            s_pos[b] = acc;
+            acc += s_hist[b];
+        }
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += 1024u) order[atomicAdd(&s_pos[255u - unsigned(cost[i] * 255ull / mx)], 1u)] = i;
+    __syncthreads();
+    for (unsigned i = tid; i < n; i += 1024u) cost[i] = 0u;
+}
+cudaError_t launch_block_order(unsigned* d_cost, unsigned* d_order, unsigned n, cudaStream_t s) {
+    block_order_kernel<<<1, 1024, 0, s>>>(d_cost, d_order, n);
+    return cudaGetLastError();
+}
+
 template <class IO> struct IsPeers { static constexpr bool value = false; };
 template <> struct IsPeers<RayIOPeers> { static constexpr bool value = true; };
 
@@ -365,10 +419,20 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
     constexpr int BS = ray_block(LIGHT), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;   // block tile = (8*WX) x (4*WY) pixels
     size_t i;
     bool valid;
+    constexpr bool ORDERED = TILED && (LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED;   // heaviest-first block dispatch (block_order_kernel)
+    unsigned lb = 0;
+    long long t_start = 0;
     if (TILED) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int x = blockIdx.x * (8 * WX) + (warp % WX) * 8 + (lane & 7);
-        const int y = blockIdx.y * (4 * WY) + (warp / WX) * 4 + (lane >> 3);
+        unsigned bx = blockIdx.x, by = blockIdx.y;
+        if (ORDERED) {
+            lb = logical_block(io);
+            bx = lb % gridDim.x;
+            by = lb / gridDim.x;
+            t_start = clock64();
+        }
+        const int x = bx * (8 * WX) + (warp % WX) * 8 + (lane & 7);
+        const int y = by * (4 * WY) + (warp / WX) * 4 + (lane >> 3);
         valid = x < c.fw && y < c.fh;
         i = size_t(y) * c.fw + x;
     } else {
@@ -402,6 +466,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
         const bool disc = shade_ray<MODEL, LIGHT>(c, mk3(od.x, od.y, od.z), mk3(dj.x, dj.y, dj.z), od.w, dj.w, out);
         store_rgba(io, i, out);
         if (io.discard) io.discard[i] = disc ? 1 : 0;
+        if (ORDERED) record_block_cost(io, lb, t_start);
     }
     peer_done(io);
 }
@@ -481,21 +546,33 @@ __device__ __forceinline__ void frame_pixel(const DevConsts& c, const IO& io, in
 template <int MODEL, int LIGHT, class IO>
 __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr bool ORDERED = (LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED;   // heaviest-first block dispatch (block_order_kernel)
+    unsigned lb = 0, bx = blockIdx.x, by = blockIdx.y;
+    long long t_start = 0;
+    if (ORDERED) {
+        lb = logical_block(io);
+        bx = lb % gridDim.x;
+        by = lb / gridDim.x;
+        t_start = clock64();
+    }
     int x, y;
     if (IsPeers<IO>::value && (LIGHT & 3) == B200ATMO_LIGHT_NONE) {
         // peer stores of a scatter-only frame are NVLink-bound, not issue-bound: a warp covers 16x2 pixels, so a tile row is one
         // 256-byte (float4) / 128-byte (half4) run instead of 128 / 64 bytes — the ncu NVLink counters show 19 % / 41 % protocol
         // bytes on top of the pixels for the 8x4 shape (profiles/r02/nvlink_counters.txt). Same 16x8 block tile, same pixels.
-        x = blockIdx.x * 16 + (lane & 15);
-        y = c.row_begin + blockIdx.y * c.row_pitch + warp * 2 + (lane >> 4);
+        x = bx * 16 + (lane & 15);
+        y = c.row_begin + by * c.row_pitch + warp * 2 + (lane >> 4);
     } else {
-        x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-        y = c.row_begin + blockIdx.y * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
+        x = bx * 16 + (warp & 1) * 8 + (lane & 7);
+        y = c.row_begin + by * c.row_pitch + (warp >> 1) * 4 + (lane >> 3);
     }
     const bool valid = x < c.fw && y < c.row_end;
     if (!IsPeers<IO>::value && !valid) return;   // the peers kernels keep every thread for the fused hand-shake
     peer_begin(io);
-    if (valid) frame_pixel<MODEL, LIGHT>(c, io, x, y);
+    if (valid) {
+        frame_pixel<MODEL, LIGHT>(c, io, x, y);
+        if (ORDERED) record_block_cost(io, lb, t_start);
+    }
     peer_done(io);
 }
 
@@ -581,6 +658,16 @@ template <class IO> static cudaError_t launch_frame_t(const DevConsts& c, const 
     light_mode = light_template_arg(c, light_mode);
     B200ATMO_DISPATCH(render_frame_kernel, grid, IO, c, io);
     return cudaGetLastError();
+}
+unsigned frame_grid_blocks(const DevConsts& c) {
+    const int rows = c.row_end - c.row_begin;
+    if (rows <= 0 || c.fw <= 0 || c.row_pitch <= 0) return 0u;
+    return unsigned((c.fw + 15) / 16) * unsigned((rows + c.row_pitch - 1) / c.row_pitch);
+}
+unsigned rays2d_grid_blocks(int w, int h) {
+    constexpr int BS = ray_block(B200ATMO_LIGHT_RAYMARCHED), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;
+    if (w <= 0 || h <= 0) return 0u;
+    return unsigned((w + 8 * WX - 1) / (8 * WX)) * unsigned((h + 4 * WY - 1) / (4 * WY));
 }
 cudaError_t launch_render_rays(const DevConsts& c, const RayIO& io, int scatter_model, int light_mode, cudaStream_t s) {
     return launch_rays_t(c, io, scatter_model, light_mode, s);

@@ -66,7 +66,7 @@ extern "C" {
 // rays: od/dj float4 SoA of n_warps*32 rays (warp w = rays [32w, 32w+32)); out[16] receives the accumulators
 void warp_model_run(const B200AtmoParams* p, const B200AtmoFrame* fr, const float* lut_pad, const float* cube_pad, int cube_res,
                     const float* shape_pad, int nx, int ny, int nz, int cloud_steps, const float* od, const float* dj,
-                    size_t n_warps, const double* costs8, double* out) {
+                    size_t n_warps, const double* costs8, double* out, double* per_warp /* nullable: per-thread-strategy cost of each warp */) {
     std::vector<float4> cube_cells, shape_cells;
     const int rc = cube_res + 1;
     cube_cells.resize(size_t(6) * rc * rc);
@@ -99,6 +99,8 @@ void warp_model_run(const B200AtmoParams* p, const B200AtmoFrame* fr, const floa
     Acc A;
     const f3 C = ld3(c.C), sun = ld3(c.sun_dir_model);
     for (size_t w = 0; w < n_warps; ++w) {
+        const double cost_before = A.per_thread;
+        if (per_warp) per_warp[w] = 0.0;
         // per-lane march set-up (render_clouds + raymarch_cloud prologue)
         bool act[32];
         f3 pos[32], dstep[32];
@@ -179,6 +181,7 @@ void warp_model_run(const B200AtmoParams* p, const B200AtmoFrame* fr, const floa
                 }
             }
         }
+        if (per_warp) per_warp[w] = A.per_thread - cost_before;
         A.light_items += double(queue.size());
         for (size_t b = 0; b < queue.size(); b += 32) {
             const size_t e = b + 32 < queue.size() ? b + 32 : queue.size();

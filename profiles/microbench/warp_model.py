@@ -56,7 +56,7 @@ def main():
         L.warp_model_run(C.byref(p), C.byref(fr), hs.lut_pad.ctypes.data_as(C.c_void_p), hs.cube_pad.ctypes.data_as(C.c_void_p),
                          C.c_int(hs.cube_res), hs.shape_pad.ctypes.data_as(C.c_void_p), C.c_int(hs.nx), C.c_int(hs.ny), C.c_int(hs.nz),
                          C.c_int(a.cloud_steps), s_od.ctypes.data_as(C.c_void_p), s_dj.ctypes.data_as(C.c_void_p),
-                         C.c_size_t(len(sel) // 32), costs, out)
+                         C.c_size_t(len(sel) // 32), costs, out, None)
         pt, lq, ideal, ls, l1, l2, l3, ws, wh, items, batches = out[:11]
         print(f"== {a.width}x{a.height} camera {a.camera}, {a.cloud_steps} cloud steps x 6 light steps, warp = {name}; {len(sel) // 32} warps sampled")
         print(f"   marching lanes per warp-step {ls / max(ws, 1):.2f}/32; in shell {l1 / max(ls, 1):.3f}, shape fetched {l2 / max(ls, 1):.3f}, density>0 {l3 / max(ls, 1):.4f} of lane-steps")

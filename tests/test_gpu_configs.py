@@ -393,3 +393,70 @@ def test_fused_handshake_and_flag_calls_on_one_gpu(cuda_ctx_factory):
     bad.sync.n_done_flags = 1
     with pytest.raises(B200AtmoError):
         ctx.render_rays_peers(fr, d_od, d_dj, h * w, bad)
+
+
+def test_heaviest_first_block_dispatch_keeps_every_pixel(cuda_ctx_factory):
+    """Raymarched-cloud launches learn a heaviest-first dispatch order of their blocks from the previous launch with the same
+    geometry on the same stream (block_order_kernel). The order is a permutation of the blocks, so the first (unordered) and
+    every later (ordered) launch must write the same bits — frame API (full frame, row bands), tile-mapped ray batch, peer
+    frames (interleaved), RGBA16F, several geometries alternating on one stream, two streams."""
+    torch = _torch()
+    ctx = cuda_ctx_factory()
+    p = scenes.demo_params()
+    _setup(ctx, p, 8, 48, abi.LIGHT_RAYMARCHED)
+    ref_ctx = cuda_ctx_factory()
+    _setup(ref_ctx, p, 8, 48, abi.LIGHT_RAYMARCHED)
+    s2 = torch.cuda.Stream()
+    for (w, h, camname) in ((333, 187, "A"), (256, 144, "C")):
+        cam = _camera(camname, w, h, p)
+        d_depth = torch.from_numpy(scenes.synth_depth(cam, p, w, h)).cuda()
+        want = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+        wdisc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+        ref_ctx.render_frame(cam, d_depth, w, h, want, wdisc)            # a fresh context's first launch: blockIdx order
+        d_od = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+        d_dj = torch.empty((h * w, 4), dtype=torch.float32, device="cuda")
+        fr = ctx.make_rays(cam, d_depth, w, h, d_od, d_dj)
+        torch.cuda.synchronize()
+        for rep in range(4):
+            n0 = ctx.launch_count
+            a = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+            ad = torch.full((h, w), 9, dtype=torch.uint8, device="cuda")
+            ctx.render_frame(cam, d_depth, w, h, a, ad)
+            assert ctx.launch_count == n0 + 2                             # the render kernel + the sort of its block costs
+            b = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+            ctx.render_rays(fr, d_od, d_dj, h * w, b, None, grid=(w, h))
+            c16 = torch.full((h, w, 4), -7.0, dtype=torch.float16, device="cuda")
+            ctx.render_frame(cam, d_depth, w, h, c16, None, rgba_format=abi.COLOR_RGBA16F)
+            banded = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+            for (r0, r1) in ((0, 50), (50, h)):
+                ctx.render_frame(cam, d_depth, w, h, banded, None, row_begin=r0, row_end=r1)
+            peers = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+            t = sharding.peer_targets([peers.data_ptr()])
+            for g in range(3):
+                ctx.render_frame_peers_interleaved(cam, d_depth, w, h, t, g, 3)
+            other = torch.full((h, w, 4), -7.0, dtype=torch.float32, device="cuda")
+            s2.wait_stream(torch.cuda.current_stream())
+            ctx.render_frame(cam, d_depth, w, h, other, None, stream=s2.cuda_stream)
+            torch.cuda.synchronize()
+            for name, got in (("frame", a), ("rays2d", b), ("bands", banded), ("peers", peers), ("stream2", other)):
+                assert torch.equal(got, want), f"{name}, launch {rep}, {w}x{h}"
+            assert torch.equal(ad, wdisc) and torch.equal(c16, want.to(torch.float16))
+    # host paths (their own streams and staging)
+    w, h = 333, 187
+    cam = _camera("A", w, h, p)
+    depth = scenes.synth_depth(cam, p, w, h)
+    want_h = np.empty((h, w, 4), np.float32)
+    ref_ctx.render_frame_host(cam, depth, w, h, want_h, None)
+    for rep in range(3):
+        got_h = np.full((h, w, 4), -7.0, np.float32)
+        ctx.render_frame_host(cam, depth, w, h, got_h, None)
+        assert np.array_equal(got_h.view(np.uint32), want_h.view(np.uint32))
+    pinned = [torch.full((h, w, 4), -7.0, dtype=torch.float32).pin_memory() for _ in range(3)]
+    hdep = torch.from_numpy(depth).pin_memory()
+    for k in range(9):
+        ctx.frame_wait(k % 3)
+        ctx.render_frame_host_submit(cam, hdep, w, h, pinned[k % 3], None, slot=k % 3)
+    for sl in range(3):
+        ctx.frame_wait(sl)
+    for b in pinned:
+        assert np.array_equal(b.numpy().view(np.uint32), want_h.view(np.uint32))

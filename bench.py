@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-configs", action="store_true", help="skip the cfg3 / cfg4 sub-results (N=1)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling runs (N>1)")
+    ap.add_argument("--quick-delivery", action="store_true", help="N>1: only the headline delivery mode and the NCCL baseline (profiling runs)")
     ap.add_argument("--e2e-steps", type=int, default=60)
     return ap.parse_args()
 
@@ -784,6 +785,8 @@ def measure_delivery(torch, dist, a, R, rank, world, timed_ms, steps):
              ("allgather_fp32", dict(rgba_format=abi.COLOR_RGBA32F)),
              ("allgather_fp32_multicast", dict(rgba_format=abi.COLOR_RGBA32F, use_multicast=True)),
              ("allgather_rgba16f_tma", dict(rgba_format=abi.COLOR_RGBA16F, use_tma=True))]
+    if a.quick_delivery:
+        modes = modes[:1]
     for label, kw in modes:
         try:
             tiles = SymmetricTiles(world, n_rays, dev, **kw)

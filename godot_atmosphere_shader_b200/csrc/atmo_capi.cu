@@ -80,7 +80,8 @@ struct b200atmo_ctx {
         TableEntry e[kTableEntries];
         OrderEntry o[kOrderEntries];
     } tables[kTableStreams];
-    bool block_order_enabled = true;    // B200ATMO_BLOCK_ORDER=0 switches it off (A/B measurements)
+    int block_order_enabled = 1;        // B200ATMO_BLOCK_ORDER=0 switches it off (A/B measurements); 2 = also for the cheap light
+                                        // (needs a library built with -DB200ATMO_ORDER_CHEAP=1)
     uint64_t table_tick = 0;
     uint64_t table_builds = 0;
     // fused completion signal of the peers kernels: a ring of block counters (zero between launches; each launch takes the
@@ -303,7 +304,7 @@ int b200atmo_create(int cuda_device, b200atmo_ctx** out) {
     b200atmo_ctx* ctx = new (std::nothrow) b200atmo_ctx();
     if (!ctx) return fail(nullptr, B200ATMO_E_NOMEM, "b200atmo_create: out of host memory");
     ctx->device = cuda_device;
-    if (const char* e = std::getenv("B200ATMO_BLOCK_ORDER")) ctx->block_order_enabled = std::atoi(e) != 0;
+    if (const char* e = std::getenv("B200ATMO_BLOCK_ORDER")) ctx->block_order_enabled = std::atoi(e);
     b200atmo_default_params(&ctx->params);
     DeviceGuard g(cuda_device);
     auto bail = [&](int code) {
@@ -613,7 +614,9 @@ static int frame_tables(b200atmo_ctx* ctx, const DevConsts& c, RayIO& io, cudaSt
 static b200atmo_ctx::OrderEntry* block_order_begin(b200atmo_ctx* ctx, cudaStream_t s, int kind, const DevConsts& c, unsigned n, RayIO& io) {
     io.block_order = nullptr;
     io.block_cost = nullptr;
-    if (!ctx->block_order_enabled || ctx->variant.light_mode != B200ATMO_LIGHT_RAYMARCHED || n < 2u) return nullptr;
+    const bool wanted = ctx->variant.light_mode == B200ATMO_LIGHT_RAYMARCHED ||
+                        (ctx->block_order_enabled == 2 && ctx->variant.light_mode == B200ATMO_LIGHT_CHEAP);
+    if (!ctx->block_order_enabled || !wanted || n < 2u) return nullptr;
     b200atmo_ctx::TableStream* ts = nullptr;
     for (auto& t : ctx->tables)
         if (t.used && t.stream == s) { ts = &t; break; }

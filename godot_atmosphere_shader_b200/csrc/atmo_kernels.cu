@@ -327,6 +327,12 @@ __device__ __forceinline__ void peer_done(const RayIOPeers& io) {
 // bins, one 1024-thread block) and clears the costs. The k-th dispatched block renders logical block block_order[k]: a
 // permutation of the blocks — pixels are untouched. Only the raymarched-light kernels use it (their blocks are long enough).
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef B200ATMO_ORDER_CHEAP
+#define B200ATMO_ORDER_CHEAP 0      // tuning knob: also order the cheap-light cloud kernels (with B200ATMO_BLOCK_ORDER=2)
+#endif
+__host__ __device__ constexpr bool uses_block_order(int light) {
+    return (light & 3) == B200ATMO_LIGHT_RAYMARCHED || (B200ATMO_ORDER_CHEAP && (light & 3) == B200ATMO_LIGHT_CHEAP);
+}
 __device__ __forceinline__ unsigned logical_block(const RayIO& io) {
     unsigned lb = blockIdx.y * gridDim.x + blockIdx.x;
     if (io.block_order) lb = __ldg(io.block_order + lb);
@@ -419,7 +425,7 @@ __global__ void B200ATMO_RAY_BOUNDS(LIGHT) render_rays_kernel(const __grid_const
     constexpr int BS = ray_block(LIGHT), WX = BS >= 64 ? 2 : 1, WY = BS / 32 / WX;   // block tile = (8*WX) x (4*WY) pixels
     size_t i;
     bool valid;
-    constexpr bool ORDERED = TILED && (LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED;   // heaviest-first block dispatch (block_order_kernel)
+    constexpr bool ORDERED = TILED && uses_block_order(LIGHT);   // heaviest-first block dispatch (block_order_kernel)
     unsigned lb = 0;
     long long t_start = 0;
     if (TILED) {
@@ -546,7 +552,7 @@ __device__ __forceinline__ void frame_pixel(const DevConsts& c, const IO& io, in
 template <int MODEL, int LIGHT, class IO>
 __global__ void __launch_bounds__(kBlock) render_frame_kernel(const __grid_constant__ DevConsts c, const IO io) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr bool ORDERED = (LIGHT & 3) == B200ATMO_LIGHT_RAYMARCHED;   // heaviest-first block dispatch (block_order_kernel)
+    constexpr bool ORDERED = uses_block_order(LIGHT);   // heaviest-first block dispatch (block_order_kernel)
     unsigned lb = 0, bx = blockIdx.x, by = blockIdx.y;
     long long t_start = 0;
     if (ORDERED) {

@@ -223,6 +223,9 @@ int b200atmo_render_rays_host(b200atmo_ctx* ctx, const B200AtmoFrame* frame,
 int b200atmo_render_frame(b200atmo_ctx* ctx, const B200AtmoCamera* cam, const float* d_depth,
                           int w, int h, int row_begin, int row_end,
                           float* d_rgba, uint8_t* d_discard, void* stream);
+/* Scheduling note (no effect on any pixel): with B200ATMO_LIGHT_RAYMARCHED the frame calls and b200atmo_render_rays_2d remember,
+ * per stream and launch geometry, how long every thread block of the previous launch ran and dispatch the next launch's blocks
+ * longest-first (one extra 10-us kernel per launch). Environment B200ATMO_BLOCK_ORDER=0 switches it off. */
 /* Same as b200atmo_render_frame, but the result is alpha-blended straight into the frame's colour buffer, which is what
  * the reference's `render_mode unshaded` + default blend_mix does in the ROP (planet_atmosphere_*.gdshader:2):
  *   color.rgb = ALBEDO * ALPHA + color.rgb * (1 - ALPHA)   for every non-discarded pixel;  color.a is left untouched.

@@ -23,6 +23,15 @@
 
 #include "atmo_internal.h"
 
+// B200ATMO_LITERAL: audit build — every round-2 shortcut that is claimed to be bit-identical is replaced by the literal form
+// (two-instruction expressions instead of the exact FMA folds, the plain shell test instead of hc_min, the shader's seventh
+// density evaluation in the light march, the literal density bound test and shape mix). tests/test_hostsim_logic.py compiles the
+// host build both ways and requires identical bits; profiles/build_variants.sh can do the same for the GPU library.
+#ifdef B200ATMO_LITERAL
+#define B200ATMO_EXACT_FOLDS 0
+#define B200ATMO_NO_HCMIN 1
+#define B200ATMO_LIGHT_RESAMPLE_FIRST 1
+#endif
 // tuning knobs (defaults chosen by profiles/tune_scatter.sh on B200)
 #ifndef B200ATMO_SCATTER_UNROLL
 #define B200ATMO_SCATTER_UNROLL 8
@@ -468,10 +477,18 @@ template <bool POW2> B200_DEV float cloud_density(const DevConsts& c, f3 p, floa
     // and the clamped density is exactly 0. ~3/4 of the in-shell samples of the demo scene end here.
     // (c.dens_y_min = the largest y with y*50 - 20 <= 0 in fp32, found on the host: the same decision as evaluating
     // (..)*hc*50 - 20 > 0 with two instructions less)
+#ifdef B200ATMO_LITERAL
+    if (!((c.hot.shape_hi_m01 + cov_term) * hc * 50.0f - 20.0f > 0.0f)) return 0.0f;
+#else
     if (!((c.hot.shape_hi_m01 + cov_term) * hc > c.hot.dens_y_min)) return 0.0f;
+#endif
     const float tex = sample_shape<POW2>(c.hot.shape_cells, c.hot.nx, c.hot.ny, c.hot.nz, p.x * c.hot.shape_scale,
                                    p.y * c.hot.shape_scale, p.z * c.hot.shape_scale);
-    float shape = c.hot.shape_mix0 + tex * c.hot.shape_factor;                         // mix(0.5, tex, factor) :48-50; 0.5*(1-factor) from the host
+#ifdef B200ATMO_LITERAL
+    float shape = mixf(0.5f, tex, c.hot.shape_factor);                         // :48-50
+#else
+    float shape = c.hot.shape_mix0 + tex * c.hot.shape_factor;                 // mix(0.5, tex, factor) :48-50; 0.5*(1-factor) from the host
+#endif
     if (c.hot.shape_invert) shape = 1.0f - shape;                              // :57-59
     // detail = 0.5 (CLOUDS_ALWAYS_LOW_QUALITY, main:49) => 0.2*detail = 0.1 (same fp32 product)
     float density = (shape - 0.2f * 0.5f + cov_term) * hc;                     // :61

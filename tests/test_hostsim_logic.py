@@ -129,3 +129,59 @@ def test_device_logic_matches_the_compiled_reference(scene, shader):
         ref, rdisc = R.render_frame(p, var, cam, otex, depth, w, h, shader=shader)
         assert np.array_equal(gdisc.reshape(h, w), rdisc), f"camera {k}"
         Hh.assert_rgba_close(got.reshape(h, w, 4), ref, what=f"{shader} camera {k}")
+
+
+def test_round2_shortcuts_are_bit_identical_to_the_literal_forms(tmp_path):
+    """The device code compiled for the host twice: as shipped, and with -DB200ATMO_LITERAL (no exact FMA folds, the plain
+    shell test instead of the hc_min rim bound, the literal density bound test and shape mix, and the shader's seventh density
+    evaluation at the first light sample). Both must produce the same bits for every variant on the demo scene (cameras A and
+    C, power-of-two and other texture sizes) and on random scenes — the claim behind 'bit-identical by construction'."""
+    import ctypes as C
+    import os
+    import subprocess
+    src = os.path.join(Hh.HERE, "hostsim", "hostsim.cpp")
+    lit = str(tmp_path / "libhostsim_literal.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-Wno-unused-function",
+                           "-Wno-unused-variable", "-x", "c++", "-shared", "-DB200ATMO_LITERAL", "-o", lit, src])
+    L = C.CDLL(lit)
+
+    def literal(hs, params, variant, frame, od, dj):
+        n = od.shape[0]
+        rgba = np.empty((n, 4), np.float32)
+        disc = np.empty((n,), np.uint8)
+        var = (C.c_int32 * 4)(variant.scatter_model, variant.scatter_steps, variant.cloud_steps, variant.light_mode)
+        ts = hs.struct()
+        L.hostsim_render_rays(C.byref(params), var, C.byref(frame), C.byref(ts), od.ctypes.data_as(C.c_void_p), dj.ctypes.data_as(C.c_void_p),
+                              C.c_size_t(n), rgba.ctypes.data_as(C.c_void_p), disc.ctypes.data_as(C.c_void_p))
+        return rgba, disc
+
+    cases = []
+    p = scenes.demo_params()
+    for tex_sizes in ((32, 64), (24, 48)):                     # power-of-two textures select the fused-coordinate instantiation
+        shape, cube, bn = scenes.shape_texture(tex_sizes[0], seed=1), scenes.coverage_cubemap(tex_sizes[1], seed=1), scenes.blue_noise_tile()
+        lut = O.bake_lut(p)
+        hs = Hh.HostsimScene(lut, shape, cube, bn)
+        otex = O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+        for cam in (scenes.camera_a(96, 54), scenes.camera_c(96, 54, p)):
+            depth = scenes.synth_depth(cam, p, 96, 54)
+            od, dj, fr = O.make_rays(p, cam, otex, depth, 96, 54)
+            cases.append((hs, p, fr, od, dj))
+    for seed in range(4):
+        q, cam = Hh.random_scene(seed)
+        shape, cube, bn = Hh.demo_textures()
+        lut = O.bake_lut(q)
+        hs = Hh.HostsimScene(lut, shape, cube, bn)
+        otex = O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+        depth = scenes.synth_depth(cam, q, 72, 48)
+        od, dj, fr = O.make_rays(q, cam, otex, depth, 72, 48)
+        cases.append((hs, q, fr, od, dj))
+    lit_cloud_pixels = 0
+    for hs, q, fr, od, dj in cases:
+        for variant in (O.variant(8, 32, 1), O.variant(8, 40, 2)):
+            a, ad = hs.render_rays(q, variant, fr, od, dj)
+            b, bd = literal(hs, q, variant, fr, od, dj)
+            assert np.array_equal(ad, bd)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"variant {variant.cloud_steps}/{variant.light_mode}: shortcut build differs from the literal build"
+            plain, _ = hs.render_rays(q, O.variant(8, 0, 0), fr, od, dj)
+            lit_cloud_pixels += int((np.abs(a - plain).max(axis=1) > 0).sum())
+    assert lit_cloud_pixels > 20000        # the comparison really exercised the cloud paths

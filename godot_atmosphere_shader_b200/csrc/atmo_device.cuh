@@ -25,7 +25,7 @@
 
 // B200ATMO_LITERAL: audit build — every round-2 shortcut that is claimed to be bit-identical is replaced by the literal form
 // (two-instruction expressions instead of the exact FMA folds, the plain shell test instead of hc_min, the shader's seventh
-// density evaluation in the light march, the literal density bound test and shape mix). tests/test_hostsim_logic.py compiles the
+// density evaluation in the light march, the literal density bound test and shape mix). The CPU test suite compiles the
 // host build both ways and requires identical bits; profiles/build_variants.sh can do the same for the GPU library.
 #ifdef B200ATMO_LITERAL
 #define B200ATMO_EXACT_FOLDS 0

@@ -89,3 +89,29 @@ def test_peer_targets_validation():
         sharding.peer_targets([0x1000] * (abi.MAX_PEERS + 1))
     with pytest.raises(ValueError):
         sharding.peer_targets([0x1000, 0])
+
+
+def test_interleaved_row_tiles_partition():
+    """The interleaved strong-scaling shard (b200atmo_render_frame_peers_interleaved): rank g owns the 8-row tiles g, g+G, ...;
+    together the ranks own every row exactly once, also when the height is not a multiple of 8 or there are more ranks than tiles."""
+    import numpy as np
+
+    from godot_atmosphere_shader_b200.sharding import interleaved_rows
+    for h in (1, 7, 8, 9, 54, 121, 1080, 2160):
+        for world in (1, 2, 3, 8):
+            owned = np.concatenate([interleaved_rows(h, r, world) for r in range(world)])
+            assert sorted(owned.tolist()) == list(range(h)), (h, world)
+            sizes = [len(interleaved_rows(h, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 8
+    rows = interleaved_rows(2160, 3, 8)
+    assert rows[0] == 24 and rows[8] == 24 + 64 and len(rows) == 8 * len(range(3, 270, 8))
+
+
+def test_peer_targets_formats_and_hand_shake_block():
+    """B200AtmoPeerTargets as sharding.peer_targets fills it: tile format, no hand-shake unless asked for."""
+    from godot_atmosphere_shader_b200 import abi, sharding
+    t = sharding.peer_targets([0x1000, 0x2000], rgba_format=abi.COLOR_RGBA16F, elem_offset=10, first_peer=5, use_tma=True)
+    assert t.rgba_format == abi.COLOR_RGBA16F and t.first_peer == 1 and t.use_tma == 1 and t.elem_offset == 10
+    y = t.sync
+    assert (y.n_done_flags, y.n_consumed_flags, y.n_credit, y.n_wait) == (0, 0, 0, 0)
+    assert sharding.peer_targets([0x1000]).rgba_format == abi.COLOR_RGBA32F

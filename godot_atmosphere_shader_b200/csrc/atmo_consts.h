@@ -91,6 +91,27 @@ inline float cloud_dens_y_min() {
     return f;
 }
 
+// Squares of two radii r_u < r_o such that a march position whose exact distance from the planet centre is below r_u or above
+// r_o has density exactly 0 with room to spare: outside the shell, or in its bottom / top rim where height_curve <= hc_min
+// (cloud_hc_min). The room (1e-6 * (steps + 64) relative) covers the rounding the shader's `pos += dir * step` accumulates
+// over `steps` additions (<= steps * 1.1e-7 relative) and that of the per-ray quadratics that use these bounds
+// (raymarch_cloud) about ten times over. under = 0 switches the skip off (degenerate shells, absurd step counts).
+inline void cloud_skip_r2(float bottom_h, float thickness, float hc_min, int steps, float& under_r2, float& over_r2) {
+    under_r2 = 0.0f;
+    over_r2 = 3.0e38f;
+    if (!(bottom_h > 0.0f) || !(thickness > 0.0f) || steps > 100000) return;
+    const double s = std::sqrt(std::fmax(0.0, 1.0 - double(std::fmin(std::fmax(hc_min, 0.0f), 1.0f))));
+    const double room = 1e-6 * (double(steps) + 64.0);
+    const double r_u = (double(bottom_h) + double(thickness) * (1.0 - s) * 0.5) * (1.0 - room);   // height_curve(hr) <= hc_min for hr <= (1 - s)/2
+    const double r_o = (double(bottom_h) + double(thickness) * (1.0 + s) * 0.5) * (1.0 + room);   // ... and for hr >= (1 + s)/2
+    if (!(r_u > 0.0) || !(r_o * r_o < 1.0e38)) return;
+    float u = float(r_u * r_u), o = float(r_o * r_o);
+    while (double(u) > r_u * r_u) u = std::nextafterf(u, 0.0f);
+    while (double(o) < r_o * r_o) o = std::nextafterf(o, 3.0e38f);
+    under_r2 = u;
+    over_r2 = o;
+}
+
 // The packed copy the cloud loops read (CloudHot, atmo_internal.h); call after any of its sources changed.
 inline void consts_pack_cloud_hot(DevConsts& c) {
     CloudHot& h = c.hot;
@@ -115,6 +136,8 @@ inline void consts_pack_cloud_hot(DevConsts& c) {
     h.nx = c.shape_nx;
     h.ny = c.shape_ny;
     h.nz = c.shape_nz;
+    cloud_skip_r2(c.cloud_bottom_h, c.cloud_thickness, c.hc_min, c.cloud_steps, h.under_r2, h.over_r2);
+    for (float& x : h.pad_) x = 0.0f;
 }
 
 // Uniform-only part (everything that does not depend on the frame).

@@ -450,6 +450,9 @@ B200_UNROLL(2)
 // ------------------------------------------------------------------------------------------------
 // include/cloud_funcs.gdshaderinc
 // ------------------------------------------------------------------------------------------------
+#ifdef B200ATMO_STEP_STATS
+static long long b200atmo_step_stats_skipped = 0;
+#endif
 // height_ratio (:36-37, :95-96, :111-112): (|p| - bottom) / (top - bottom)
 B200_DEV float cloud_height_ratio(const DevConsts& c, float len) {
     return div_refined(len - c.hot.bottom_h, c.hot.thickness, c.hot.inv_thickness);
@@ -555,8 +558,74 @@ template <int LIGHT> B200_DEV f2 raymarch_cloud(const DevConsts& c, f3 o, f3 d, 
     float T_clamped = 1.0f;  // total_transmittance (:222-223)
     float T_alpha = 1.0f;    // 1 - alpha (:228 telescopes to a product of transmittances)
     float total_light = 0.0f;
+    // Exact skip of the steps that cannot meet cloud: the run that passes UNDER the shell (a ray that reaches the ground, or
+    // crosses the shell twice, spends a third of its steps there) and the steps in the empty rim at the TOP of the shell
+    // where the march starts and ends. The positions are pos + i*dstep up to the rounding of the additions, so
+    // |pos_i|^2 < under_r2 and |pos_i|^2 > over_r2 are quadratic inequalities in i, solved once per ray. The two radii
+    // (atmo_consts.h: cloud_skip_r2) sit far enough outside the band that can hold cloud to absorb that rounding and the fp32
+    // error of this solve (the guard on |pos|^2 keeps the latter below 5e-6 * r^2), and one whole step is given away at
+    // every end on top of that: in a skipped step the shader's density is exactly 0, so nothing but `pos += dstep` happens.
+    // The march becomes  skip | evaluate [b0, e0) | skip | evaluate [b1, e1) | (the rest only moves pos: dropped).  On the GPU
+    // the four bounds are widened to the union over the lanes that march together, so the trip counts are warp-uniform and
+    // the evaluated loop carries no per-step test (8x4 pixel tiles: 1/3 of the warp-steps of the cfg4 frame have no lane
+    // in the shell).
+    int b0 = 0, e0 = steps, b1 = steps, e1 = steps;
+#if !defined(B200ATMO_LITERAL) && !defined(B200ATMO_NO_UNDER_SKIP)
+    {
+        const float qa = dot3(dstep, dstep), qb = dot3(pos, dstep), q0 = dot3(pos, pos);
+        if (qa > 1e-30f && q0 < 4.0f * c.hot.under_r2) {
+            const float ia = 1.0f / qa, nsteps = float(steps);
+            int in_b = 0, in_e = steps;          // steps that may be below over_r: [in_b, in_e)
+            const float disc_o = qb * qb - qa * (q0 - c.hot.over_r2);
+            if (!(disc_o > 0.0f)) in_e = 0;      // the whole line stays above the shell (NaN: nothing is finite, nothing to march)
+            else {
+                const float sq = sqrtf(disc_o);
+                const float lo = (-qb - sq) * ia, hi = (-qb + sq) * ia;   // |pos + x*dstep|^2 < over_r2 for x in (lo, hi)
+                if (fabsf(lo) < 1e9f && fabsf(hi) < 1e9f) {
+                    in_b = int(fminf(fmaxf(floorf(lo) - 1.0f, 0.0f), nsteps));
+                    in_e = int(fminf(fmaxf(ceilf(hi) + 2.0f, 0.0f), nsteps));
+                }
+            }
+            int un_b = steps, un_e = steps;      // steps surely below under_r: [un_b, un_e)
+            const float disc_u = qb * qb - qa * (q0 - c.hot.under_r2);
+            if (disc_u > 0.0f) {
+                const float sq = sqrtf(disc_u);
+                const float lo = (-qb - sq) * ia, hi = (-qb + sq) * ia;   // |pos + x*dstep|^2 < under_r2 for x in (lo, hi)
+                if (fabsf(lo) < 1e9f && fabsf(hi) < 1e9f) {
+                    const float first = fmaxf(ceilf(lo) + 1.0f, 0.0f), end = fminf(floorf(hi), nsteps);
+                    if (end > first) { un_b = int(first); un_e = int(end); }
+                }
+            }
+            if (!(disc_o == disc_o) || !(disc_u == disc_u)) { in_b = 0; in_e = steps; un_b = un_e = steps; }   // NaN anywhere: march literally
+            b0 = in_b; e0 = un_b < in_e ? un_b : in_e;
+            b1 = un_e > in_b ? un_e : in_b; e1 = in_e;
+            if (e0 < b0) e0 = b0;
+            if (b1 < e0) b1 = e0;
+            if (e1 < b1) e1 = b1;
+#ifdef B200ATMO_STEP_STATS   // host builds only: how many steps the skip covers (so a comparison can show it was exercised)
+            b200atmo_step_stats_skipped += steps - (e0 - b0) - (e1 - b1);
+#endif
+        }
+    }
+#ifdef __CUDA_ARCH__
+    {   // widen to the lanes that are here together (any converged subset is a valid group)
+        const unsigned grp = __activemask();
+        const bool none0 = e0 <= b0, none1 = e1 <= b1;       // an empty segment must not widen the union
+        b0 = __reduce_min_sync(grp, none0 ? 0x7fffffff : b0); e0 = __reduce_max_sync(grp, none0 ? 0 : e0);
+        b1 = __reduce_min_sync(grp, none1 ? 0x7fffffff : b1); e1 = __reduce_max_sync(grp, none1 ? 0 : e1);
+        if (e0 <= b0) b0 = e0 = 0;                           // no lane has a first segment
+        if (e1 <= b1) b1 = e1 = e0;                          // ... a second one
+        if (b1 < e0) { e0 = e1 > e0 ? e1 : e0; b1 = e1 = e0; }   // the lanes' first segments reach into a second one: one segment
+    }
+#endif
+#endif
+    int i = 0;
+B200_UNROLL(1)
+    for (int seg = 0; seg < 2; ++seg) {
+    const int seg_b = seg == 0 ? b0 : b1, seg_e = seg == 0 ? e0 : e1;
+    for (; i < seg_b; ++i) pos = pos + dstep;   // :236 — outside the cloud band: density 0, transmittance 1, nothing accumulates
 B200_UNROLL(kUnroll)
-    for (int i = 0; i < steps; ++i) {
+    for (; i < seg_e; ++i) {
         float inv;
         const float len = sqrt_refined(dot3(pos, pos), inv);
         const float hr = cloud_height_ratio(c, len);
@@ -576,6 +645,7 @@ B200_UNROLL(kUnroll)
             T_alpha *= tr;                                                                    // :228
         }
         pos = pos + dstep;  // :236, exact
+    }
     }
     return f2{total_light, 1.0f - T_alpha};
 }

@@ -32,6 +32,8 @@ struct alignas(16) CloudHot {
     const float4* cube_cells;
     const float4* shape_cells;
     int cube_res, nx, ny, nz;
+    float under_r2, over_r2; // squares of two radii safely below / above the band of the shell that can hold cloud (atmo_consts.h: cloud_skip_r2)
+    float pad_[2];
 };
 
 // Everything a render kernel needs, passed by value as a __grid_constant__ kernel parameter.

@@ -39,7 +39,7 @@ struct Costs {
 struct Acc {
     double per_thread = 0, light_queue = 0, ideal = 0;
     double lanes_steps = 0, lanes_shell = 0, lanes_shape = 0, lanes_hit = 0, warp_steps = 0, warp_any_hit = 0;
-    double light_items = 0, light_batches = 0;
+    double light_items = 0, light_batches = 0, warp_steps_no_shell = 0;
 };
 
 struct Item {
@@ -164,6 +164,7 @@ void warp_model_run(const B200AtmoParams* p, const B200AtmoFrame* fr, const floa
                 pos[l] = pos[l] + dstep[l];
             }
             A.warp_steps += 1;
+            if (n1 == 0) A.warp_steps_no_shell += 1;
             A.lanes_steps += n_act; A.lanes_shell += n1; A.lanes_shape += n2; A.lanes_hit += n3;
             const double front = k.base + (n1 ? k.cube : 0) + (n2 ? k.shape : 0);
             A.per_thread += front;
@@ -192,6 +193,7 @@ void warp_model_run(const B200AtmoParams* p, const B200AtmoFrame* fr, const floa
     out[0] = A.per_thread; out[1] = A.light_queue; out[2] = A.ideal; out[3] = A.lanes_steps; out[4] = A.lanes_shell;
     out[5] = A.lanes_shape; out[6] = A.lanes_hit; out[7] = A.warp_steps; out[8] = A.warp_any_hit; out[9] = A.light_items;
     out[10] = A.light_batches;
+    out[11] = A.warp_steps_no_shell;
 }
 
 }  // extern "C"

@@ -61,6 +61,7 @@ def main():
         print(f"== {a.width}x{a.height} camera {a.camera}, {a.cloud_steps} cloud steps x 6 light steps, warp = {name}; {len(sel) // 32} warps sampled")
         print(f"   marching lanes per warp-step {ls / max(ws, 1):.2f}/32; in shell {l1 / max(ls, 1):.3f}, shape fetched {l2 / max(ls, 1):.3f}, density>0 {l3 / max(ls, 1):.4f} of lane-steps")
         print(f"   warp-steps with a hit {wh / max(ws, 1):.3f}; lanes hit in those {l3 / max(wh, 1):.2f}/32; light items {items:.0f} in {batches:.0f} batches ({items / max(batches, 1):.1f}/batch)")
+        print(f"   warp-steps with no lane in the shell {out[11] / max(ws, 1):.3f}")
         print(f"   issued warp-instr (model): per-thread {pt:.4g}  light-queue {lq:.4g} ({lq / pt:.3f}x)  ideal {ideal:.4g} ({ideal / pt:.3f}x)")
 
 

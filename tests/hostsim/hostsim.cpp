@@ -132,4 +132,15 @@ float hostsim_sqrt_refined(float x) { float inv; return sqrt_refined(x, inv); }
 float hostsim_div_refined(float a, float b) { return div_refined(a, b, 1.0f / b); }
 int hostsim_floor_frac(float x, float* frac) { return floor_frac(x, *frac); }
 
+// steps covered by the under-shell skip of raymarch_cloud since the last call (builds with -DB200ATMO_STEP_STATS; else -1)
+long long hostsim_take_skipped_steps() {
+#ifdef B200ATMO_STEP_STATS
+    const long long v = b200atmo_step_stats_skipped;
+    b200atmo_step_stats_skipped = 0;
+    return v;
+#else
+    return -1;
+#endif
+}
+
 }  // extern "C"

@@ -185,3 +185,77 @@ def test_round2_shortcuts_are_bit_identical_to_the_literal_forms(tmp_path):
             plain, _ = hs.render_rays(q, O.variant(8, 0, 0), fr, od, dj)
             lit_cloud_pixels += int((np.abs(a - plain).max(axis=1) > 0).sum())
     assert lit_cloud_pixels > 20000        # the comparison really exercised the cloud paths
+
+
+def test_under_shell_skip_is_exact_and_exercised(tmp_path):
+    """raymarch_cloud skips, per ray, the run of steps that passes under the cloud shell (a quadratic solved once per ray with
+    a guard band, csrc/atmo_device.cuh). The device code compiled for the host with the skip and with -DB200ATMO_NO_UNDER_SKIP
+    must produce the same bits — demo scene (cameras A, B, C, a far camera, step counts 16..300, both light modes), hard
+    geometry (near depth that clips the march to a sliver, huge node offsets, planets from 1 to 1000 units) and random
+    scenes — and the skip must really cover a large share of the steps of those cases."""
+    import ctypes as C
+    import os
+    import subprocess
+    src = os.path.join(Hh.HERE, "hostsim", "hostsim.cpp")
+    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-Wno-unused-function",
+              "-Wno-unused-variable", "-x", "c++", "-shared"]
+    libs = {}
+    for name, flag in (("skip", "-DB200ATMO_STEP_STATS"), ("noskip", "-DB200ATMO_NO_UNDER_SKIP")):
+        so = str(tmp_path / f"libhostsim_{name}.so")
+        subprocess.check_call(common + [flag, "-o", so, src])
+        libs[name] = C.CDLL(so)
+        libs[name].hostsim_take_skipped_steps.restype = C.c_longlong
+
+    def run(L, hs, params, variant, frame, od, dj):
+        n = od.shape[0]
+        rgba = np.empty((n, 4), np.float32)
+        disc = np.empty((n,), np.uint8)
+        var = (C.c_int32 * 4)(variant.scatter_model, variant.scatter_steps, variant.cloud_steps, variant.light_mode)
+        ts = hs.struct()
+        L.hostsim_render_rays(C.byref(params), var, C.byref(frame), C.byref(ts), np.ascontiguousarray(od).ctypes.data_as(C.c_void_p),
+                              np.ascontiguousarray(dj).ctypes.data_as(C.c_void_p), C.c_size_t(n), rgba.ctypes.data_as(C.c_void_p),
+                              disc.ctypes.data_as(C.c_void_p))
+        return rgba, disc
+
+    cases = []   # (textures, params, frame, od, dj, step counts)
+    p = scenes.demo_params()
+    shape, cube, bn = Hh.demo_textures()
+    lut = O.bake_lut(p)
+    hs = Hh.HostsimScene(lut, shape, cube, bn)
+    otex = O.Textures(lut=lut, shape=shape, cube_faces=cube, blue_noise=bn)
+    w, h = 80, 45
+    far_cam = scenes.make_camera((0.0, 30.0, 40.0 * p.planet_radius), (0.0, -0.02, -1.0), fovy_deg=8.0, aspect=w / h, near=0.5, far=1e5)
+    for cam, steps in ((scenes.camera_a(w, h), (16, 64, 128, 300)), (scenes.camera_b(w, h, p), (32, 128)), (scenes.camera_c(w, h, p), (64, 128)),
+                       (scenes.camera_c(w, h, p, pitch_deg=5.0), (128,)), (far_cam, (64, 128))):
+        depth = scenes.synth_depth(cam, p, w, h)
+        od, dj, fr = O.make_rays(p, cam, otex, depth, w, h)
+        cases.append((hs, p, fr, od, dj, steps))
+        # opaque geometry right behind the entry point of the shell: the march is clipped to a sliver (tiny steps)
+        od2 = od.copy()
+        od2[:, 3] = np.where(np.arange(len(od2)) % 3 == 0, od[:, 3] * 0.02 + 0.3, od[:, 3])
+        cases.append((hs, p, fr, od2, dj, (64,)))
+    for seed in range(10):
+        q, cam = Hh.random_scene(seed)
+        if seed % 3 == 0:                      # a node far from the world origin (large translations in view_to_model)
+            q.world_to_model[12] += 3.0e4
+            q.world_to_model[13] -= 1.0e4
+        lut_q = O.bake_lut(q)
+        hs_q = Hh.HostsimScene(lut_q, shape, cube, bn)
+        otex_q = O.Textures(lut=lut_q, shape=shape, cube_faces=cube, blue_noise=bn)
+        depth = scenes.synth_depth(cam, q, 60, 40)
+        od, dj, fr = O.make_rays(q, cam, otex_q, depth, 60, 40)
+        cases.append((hs_q, q, fr, od, dj, (48, 128)))
+    total_steps = skipped = 0
+    for hs_k, q, fr, od, dj, steps in cases:
+        for m in steps:
+            for light in (1, 2):
+                variant = O.variant(8, m, light)
+                libs["skip"].hostsim_take_skipped_steps()
+                a, ad = run(libs["skip"], hs_k, q, variant, fr, od, dj)
+                skipped += libs["skip"].hostsim_take_skipped_steps()
+                total_steps += m * len(od)
+                b, bd = run(libs["noskip"], hs_k, q, variant, fr, od, dj)
+                assert np.array_equal(ad, bd)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{m} cloud steps, light {light}: the under-shell skip changed a pixel"
+    assert libs["noskip"].hostsim_take_skipped_steps() == -1
+    assert skipped > 0.05 * total_steps, (skipped, total_steps)
